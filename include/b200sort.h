@@ -1,0 +1,156 @@
+/*
+ * b200sort.h -- C ABI of libb200sort.so, the B200 (sm_100a) key + payload sort that replaces the hot
+ * path of jonicho/simd-radix-sort.
+ *
+ * The reference has no FFI layer: its boundary is the C++20 function-template signature
+ *     simd_sort::radix_sort::sort<Up>(num, keys, payloads...)            (radixSort.hpp:1780-1783)
+ *     simd_sort::radix_sort::sort<Up>(num, DataElement<K, Ps...>*)       (radixSort.hpp:1770-1778)
+ * include/b200sort/radixSort.hpp re-declares exactly those templates and forwards every
+ * instantiation, type-erased, to the entry points below.  Anything else (ctypes, cgo, JNI ...) binds
+ * the same symbols; INTEGRATION.md shows the stubs.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.
+ *  - every array may live in HOST memory (sorted through a staged copy on the current CUDA device) or
+ *    in DEVICE memory (sorted in place on the device that owns it: the fast path).  All arrays of
+ *    one call must be on the same side.
+ *  - the sort is in place from the caller's point of view (reference: radix_sort.hpp:297-337): the
+ *    result overwrites keys/payloads/records.  Scratch (one shadow copy of every stream + per-tile
+ *    status words) comes from `workspace` or, when that is NULL, from a per-device cache owned by
+ *    the library.
+ *  - return value: 0 on success, a negative B200SORT_E* code otherwise; b200sort_last_error() gives
+ *    a thread-local human-readable message.  There is NO CPU fallback: without a usable CUDA device
+ *    every sort call fails with B200SORT_ECUDA.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device-memory
+ *    calls are asynchronous on that stream; host-memory calls return after the data is back.
+ */
+#ifndef B200SORT_H_
+#define B200SORT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SORT_VERSION 100
+
+/* key types: the ten arithmetic key types of the reference's test matrix (src/test.cpp:155-169) */
+enum {
+  B200SORT_U8 = 0, B200SORT_I8 = 1, B200SORT_U16 = 2, B200SORT_I16 = 3, B200SORT_U32 = 4,
+  B200SORT_I32 = 5, B200SORT_U64 = 6, B200SORT_I64 = 7, B200SORT_F32 = 8, B200SORT_F64 = 9
+};
+
+enum {
+  B200SORT_OK = 0,
+  B200SORT_EINVAL = -1,     /* bad key type, negative num, NULL array, mixed host/device arrays */
+  B200SORT_ESHAPE = -2,     /* payload element size not in 1..64, > 63 payload streams */
+  B200SORT_ERECORD = -3,    /* AoS record size not a power of two in [sizeof(key), 64]
+                               (the reference static_asserts this, radix_sort.hpp:318-319) */
+  B200SORT_ENOMEM = -4,     /* workspace too small / device allocation failed */
+  B200SORT_ECUDA = -5,      /* CUDA runtime error or no device; see b200sort_last_error() */
+  B200SORT_ENCCL = -6,      /* NCCL error or libnccl not loadable (multi-GPU entry points only) */
+  B200SORT_EUNSUPPORTED = -7
+};
+
+/* cmp_sorter values for the *_ex entry points (reference: template parameter CmpSorter) */
+enum {
+  B200SORT_CMP_INSERTION = 0, /* CmpSorterInsertionSort, src/cmp_sorters.hpp:18-37: full sort */
+  B200SORT_CMP_NONE = 1       /* CmpSorterNoSort, src/cmp_sorters.hpp:66-78: buckets of at most
+                                 `cmp_sort_threshold` elements are left in arbitrary internal order */
+};
+
+/* Replaces simd_sort::radix_sort::sort<Up>(num, keys, payloads...)  (radixSort.hpp:1780-1783,
+ * src/radix_sort.hpp:334-337).  payload_elem_bytes[i] in 1..64; n_payloads in 0..63. */
+int b200sort_sort_soa(void *keys, int key_type, int64_t num, int ascending, int n_payloads,
+                      void *const *payloads, const uint32_t *payload_elem_bytes, void *stream,
+                      void *workspace, size_t workspace_bytes);
+
+/* Replaces simd_sort::radix_sort::sort<Up>(num, DataElement<K, Ps...>*)  (radixSort.hpp:1770-1778,
+ * src/radix_sort.hpp:314-332).  Records of `record_bytes` bytes, key of `key_type` at byte offset 0. */
+int b200sort_sort_aos(void *records, int key_type, uint32_t record_bytes, int64_t num, int ascending,
+                      void *stream, void *workspace, size_t workspace_bytes);
+
+/* Replaces the advanced overloads sort<Up, BitSorter, CmpSorter>(cmpSortThreshold, num, ...)
+ * (src/radix_sort.hpp:297-332).  With B200SORT_CMP_INSERTION the result is the full sort whatever the
+ * threshold (as in the reference).  With B200SORT_CMP_NONE the result satisfies the reference's
+ * partial-sort contract: the array is a permutation of the input in which every maximal group of
+ * elements sharing the key bits above the point where the reference would stop recursing is
+ * contiguous and groups appear in key order. */
+int b200sort_sort_soa_ex(void *keys, int key_type, int64_t num, int ascending, int n_payloads,
+                         void *const *payloads, const uint32_t *payload_elem_bytes,
+                         int64_t cmp_sort_threshold, int cmp_sorter, void *stream, void *workspace,
+                         size_t workspace_bytes);
+int b200sort_sort_aos_ex(void *records, int key_type, uint32_t record_bytes, int64_t num, int ascending,
+                         int64_t cmp_sort_threshold, int cmp_sorter, void *stream, void *workspace,
+                         size_t workspace_bytes);
+
+/* Bytes of device scratch a call with these shapes needs (record_bytes = 0 for the SoA form, in
+ * which case n_payloads/payload_elem_bytes describe the streams; for the AoS form they are ignored). */
+size_t b200sort_workspace_bytes(int key_type, int64_t num, int n_payloads,
+                                const uint32_t *payload_elem_bytes, uint32_t record_bytes);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *b200sort_last_error(void);
+
+int b200sort_version(void);
+
+/* Number of kernels this library has launched in this process so far (monotonic; used by bench.py
+ * for its gpu_launches field). */
+uint64_t b200sort_launch_count(void);
+
+/* Tuning/ablation knobs, process-wide.  Known names: "algo" (0 auto, 1 LSD one-sweep passes,
+ * 2 hybrid MSB), "tile_cfg" (index of the scatter tile geometry), "use_match" (1 = __match_any_sync
+ * ranking, 0 = ballot ranking).  Returns 0, or B200SORT_EINVAL for an unknown name. */
+int b200sort_set_option(const char *name, int64_t value);
+int64_t b200sort_get_option(const char *name);
+
+/* What the last successful device-side sort on this thread did (for roofline accounting). */
+typedef struct b200sort_stats {
+  int64_t num;
+  uint32_t record_bytes;      /* sum of all stream element sizes */
+  uint32_t key_bytes;
+  uint32_t algo;              /* 1 LSD, 2 hybrid */
+  uint32_t passes_planned;    /* scatter passes launched */
+  uint32_t hist_sweeps;       /* key-only sweeps launched */
+  uint32_t kernel_launches;   /* kernels launched by this call */
+  uint64_t algorithmic_bytes; /* H*N*K + P*2*N*R with the planned pass counts */
+} b200sort_stats;
+int b200sort_last_stats(b200sort_stats *out);
+
+/* Releases the per-device workspace caches held by the library. */
+void b200sort_release_cache(void);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------
+ * The communicator is created by the library from an ncclUniqueId that rank 0 obtains with
+ * b200sort_mgpu_unique_id() and distributes by any means (torch.distributed, MPI, a file). */
+typedef struct b200sort_comm b200sort_comm;
+#define B200SORT_UNIQUE_ID_BYTES 128
+int b200sort_mgpu_unique_id(void *out_id_128_bytes);
+int b200sort_mgpu_comm_create(b200sort_comm **out, int world_size, int rank, const void *id_128_bytes);
+int b200sort_mgpu_comm_destroy(b200sort_comm *comm);
+
+/* Host-side splitter selection used by the multi-GPU sort (exported so that it can be tested without
+ * a GPU): given the globally reduced histogram of the top `bits` bits of the order-mapped keys
+ * (2^bits counters), writes world_size+1 bin boundaries b[0]=0 <= ... <= b[world]=2^bits such that
+ * rank r owns bins [b[r], b[r+1]) and the loads are as even as bin granularity allows. */
+int b200sort_mgpu_splitters(const uint64_t *global_hist, int bits, int world_size, uint32_t *out_bounds);
+
+/* Host-side exchange plan (also exported for GPU-less tests): number of local records destined to each
+ * rank, given this rank's own top-bits histogram and the splitters above. */
+int b200sort_mgpu_plan(const uint64_t *local_hist, int bits, int world_size, const uint32_t *bounds,
+                       uint64_t *out_send_counts);
+
+/* Distributed SoA sort.  On entry every rank holds `num_local` unsorted records in device memory; on
+ * return rank r holds *out_num_local records, sorted, all of them ordered before those of rank r+1.
+ * `capacity` is the number of records each of keys/payloads can hold (>= the largest partition; the
+ * call fails with B200SORT_ENOMEM, before moving data, if a partition would not fit). */
+int b200sort_mgpu_sort_soa(b200sort_comm *comm, void *keys, int key_type, int64_t num_local,
+                           int64_t capacity, int ascending, int n_payloads, void *const *payloads,
+                           const uint32_t *payload_elem_bytes, int64_t *out_num_local, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SORT_H_ */

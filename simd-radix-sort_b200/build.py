@@ -1,0 +1,56 @@
+"""Builds libb200sort.so (the C-ABI library of include/b200sort.h) in-tree with nvcc for sm_100a.
+
+    python simd-radix-sort_b200/build.py [--force]
+
+The library has no torch dependency; it links the CUDA runtime statically and loads NCCL lazily
+(multi-GPU entry points only).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libb200sort.so"
+SOURCES = [CSRC / "b200sort.cu"]
+HEADERS = [CSRC / "kernels.cuh", CSRC / "hybrid.cuh", CSRC / "mgpu.cuh", PKG.parent / "include" / "b200sort.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+    "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+]
+
+
+def nvcc_path() -> str:
+    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(cand).exists():
+        raise RuntimeError("nvcc not found; libb200sort.so cannot be built (there is no CPU fallback)")
+    return cand
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.exists() and p.stat().st_mtime > t for p in SOURCES + HEADERS)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    srcs = [str(s) for s in SOURCES if s.exists()]
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *srcs, "-ldl"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,560 @@
+// b200sort.cu -- host side of libb200sort.so: the C ABI of include/b200sort.h, workspace management,
+// host-array staging and the launch sequence of a sort.
+//
+// Replaces (paths under /root/reference): the public sort<> overloads and radixRecursion,
+// src/radix_sort.hpp:270-337.  There is deliberately no CPU code path in this file: if CUDA is not
+// usable every entry point fails.
+#include "../../include/b200sort.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "hybrid.cuh"
+
+namespace b200sort {
+
+// ------------------------------------------------------------------------------------------------
+// errors, options, counters
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static thread_local b200sort_stats g_last_stats{};
+static thread_local bool g_have_stats = false;
+static std::atomic<uint64_t> g_launches{0};
+
+static std::atomic<int64_t> opt_algo{0};       // 0 auto, 1 LSD, 2 hybrid
+static std::atomic<int64_t> opt_tile_cfg{-1};  // -1 auto
+static std::atomic<int64_t> opt_use_match{1};
+static std::atomic<int64_t> opt_allow_skip{1};
+static std::atomic<int64_t> opt_hist_match{1};
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(B200SORT_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static int key_bytes_of(int kt) {
+  switch (kt) {
+    case B200SORT_U8: case B200SORT_I8: return 1;
+    case B200SORT_U16: case B200SORT_I16: return 2;
+    case B200SORT_U32: case B200SORT_I32: case B200SORT_F32: return 4;
+    case B200SORT_U64: case B200SORT_I64: case B200SORT_F64: return 8;
+    default: return 0;
+  }
+}
+
+KeyOrder make_key_order(int key_type, bool ascending) {
+  const int kb = key_bytes_of(key_type);
+  const uint64_t mask = kb == 8 ? ~0ull : ((1ull << (8 * kb)) - 1);
+  const uint64_t sign = 1ull << (8 * kb - 1);
+  const bool is_signed = key_type == B200SORT_I8 || key_type == B200SORT_I16 || key_type == B200SORT_I32 ||
+                         key_type == B200SORT_I64;
+  const bool is_float = key_type == B200SORT_F32 || key_type == B200SORT_F64;
+  KeyOrder ko{0, 0};
+  if (is_signed || is_float) ko.xor_const = sign;
+  if (is_float) ko.neg_xor = mask ^ sign;
+  if (!ascending) ko.xor_const ^= mask;
+  return ko;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// tile geometries of the scatter kernel
+// ------------------------------------------------------------------------------------------------
+struct TileCfg { int threads, ipt; };
+static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 32}};
+static constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
+
+static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes) {
+  const size_t tile = (size_t)c.threads * c.ipt;
+  return tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3;
+}
+
+template <int KB, int THREADS, int IPT>
+static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match, cudaStream_t st) {
+  bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
+  for (int s = (a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == KB) ? 1 : 0; s < a.ss.n_streams; s++)
+    any = any || a.ss.streams[s].chunk_bytes < 4;
+  void (*k)(const SweepArgs);
+  if (any) k = use_match ? onesweep_kernel<KB, THREADS, IPT, true, true> : onesweep_kernel<KB, THREADS, IPT, false, true>;
+  else k = use_match ? onesweep_kernel<KB, THREADS, IPT, true, false> : onesweep_kernel<KB, THREADS, IPT, false, false>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<(unsigned)n_tiles, THREADS, smem, st>>>(a);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int KB>
+static cudaError_t launch_sweep_kb(int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match,
+                                   cudaStream_t st) {
+  switch (cfg) {
+    case 0: return launch_sweep_t<KB, 512, 16>(a, n_tiles, smem, use_match, st);
+    case 1: return launch_sweep_t<KB, 256, 16>(a, n_tiles, smem, use_match, st);
+    case 2: return launch_sweep_t<KB, 512, 8>(a, n_tiles, smem, use_match, st);
+    default: return launch_sweep_t<KB, 256, 32>(a, n_tiles, smem, use_match, st);
+  }
+}
+
+static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match,
+                                cudaStream_t st) {
+  switch (kb) {
+    case 1: return launch_sweep_kb<1>(cfg, a, n_tiles, smem, use_match, st);
+    case 2: return launch_sweep_kb<2>(cfg, a, n_tiles, smem, use_match, st);
+    case 4: return launch_sweep_kb<4>(cfg, a, n_tiles, smem, use_match, st);
+    default: return launch_sweep_kb<8>(cfg, a, n_tiles, smem, use_match, st);
+  }
+}
+
+constexpr int HIST_THREADS = 512, HIST_IPT = 8;
+
+template <int KB>
+static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, cudaStream_t st) {
+  if (use_match)
+    hist_kernel<KB, HIST_THREADS, HIST_IPT, true><<<grid, HIST_THREADS, 0, st>>>(a);
+  else
+    hist_kernel<KB, HIST_THREADS, HIST_IPT, false><<<grid, HIST_THREADS, 0, st>>>(a);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, cudaStream_t st) {
+  const int64_t tiles = (a.n + HIST_THREADS * HIST_IPT - 1) / (HIST_THREADS * HIST_IPT);
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * 4);
+  const bool m = opt_hist_match.load() != 0;
+  switch (kb) {
+    case 1: return launch_hist_t<1>(a, grid, m, st);
+    case 2: return launch_hist_t<2>(a, grid, m, st);
+    case 4: return launch_hist_t<4>(a, grid, m, st);
+    default: return launch_hist_t<8>(a, grid, m, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device properties + per-device workspace cache
+// ------------------------------------------------------------------------------------------------
+struct DevInfo { int sm_count = 0; size_t smem_optin = 0; bool ok = false; };
+static std::mutex g_mu;
+static std::map<int, DevInfo> g_dev;
+struct CacheEntry { void *ptr = nullptr; size_t bytes = 0; };
+static std::map<int, CacheEntry> g_cache;
+
+static int dev_info(int dev, DevInfo *out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  DevInfo &d = g_dev[dev];
+  if (!d.ok) {
+    int v = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    d.sm_count = v;
+    CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    d.smem_optin = (size_t)v;
+    d.ok = true;
+  }
+  *out = d;
+  return 0;
+}
+
+static int cached_workspace(int dev, size_t bytes, void **out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CacheEntry &c = g_cache[dev];
+  if (c.bytes < bytes) {
+    if (c.ptr) {
+      CUDA_TRY(cudaDeviceSynchronize());
+      CUDA_TRY(cudaFree(c.ptr));
+      c.ptr = nullptr;
+      c.bytes = 0;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(B200SORT_ENOMEM, "cudaMalloc of %zu workspace bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    c.ptr = p;
+    c.bytes = bytes;
+  }
+  *out = c.ptr;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// job description
+// ------------------------------------------------------------------------------------------------
+struct StreamDesc { void *ptr; uint32_t elem_bytes; };
+
+struct Layout {
+  size_t shadow_off[MAX_STREAMS];
+  size_t ctrl_off, ctrl_bytes;       // zeroed at the start of every sort
+  size_t ghist_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off;
+  size_t total;
+  int64_t n_tiles;
+};
+
+static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin) {
+  int cfg = (int)opt_tile_cfg.load();
+  if (cfg < 0 || cfg >= kNumTileCfgs) cfg = (kb >= 4) ? 0 : 0;
+  // fall back to a smaller tile if the staging buffer would not fit
+  while (sweep_smem_bytes(kTileCfgs[cfg], stage_bytes) > smem_optin && cfg != 1) cfg = 1;
+  return cfg;
+}
+
+static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int tile, Layout *L) {
+  size_t off = 0;
+  for (size_t s = 0; s < streams.size(); s++) {
+    L->shadow_off[s] = off;
+    off = align_up(off + (size_t)n * streams[s].elem_bytes, 256);
+  }
+  L->n_tiles = (n + tile - 1) / tile;
+  // hybrid path tiles may be smaller than the sweep tiles; size the look-back for the smallest tile used
+  L->ctrl_off = off;
+  L->ghist_off = off;               off += (size_t)8 * RADIX * 8;
+  L->tilectr_off = off;             off += MAX_PASSES * 4;
+  L->plan_off = off;                off = align_up(off + sizeof(Plan), 256);
+  L->hyb_off = off;                 off = align_up(off + sizeof(HybridCtrl), 256);
+  L->lookback_off = off;            off += (size_t)L->n_tiles * RADIX * 8;
+  L->ctrl_bytes = off - L->ctrl_off;
+  L->binbase_off = off;             off += (size_t)MAX_PASSES * RADIX * 8;
+  L->total = align_up(off, 256);
+}
+
+static uint32_t chunk_for(const void *p, uint32_t elem) {
+  // largest power of two <= 16 dividing both the address and the element size
+  uint32_t c = 16;
+  while (c > 1 && ((elem % c) != 0 || ((uintptr_t)p % c) != 0)) c >>= 1;
+  return c;
+}
+
+// Sort arrays that are all in device memory.  streams[0] carries the key at offset 0.
+static int sort_device(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams,
+                       cudaStream_t stream, void *workspace, size_t workspace_bytes) {
+  const int kb = key_bytes_of(key_type);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  DevInfo di;
+  if (int rc = dev_info(dev, &di)) return rc;
+
+  uint32_t stage_bytes = (uint32_t)kb, rec_bytes = 0;
+  StreamSet ss{};
+  ss.n_streams = (int)streams.size();
+  for (size_t s = 0; s < streams.size(); s++) {
+    const uint32_t c = chunk_for(streams[s].ptr, streams[s].elem_bytes);
+    ss.streams[s].chunk_bytes = c;
+    ss.streams[s].chunks_per_elem = streams[s].elem_bytes / c;
+    ss.streams[s].buf[0] = (unsigned char *)streams[s].ptr;
+    stage_bytes = std::max(stage_bytes, c);
+    rec_bytes += streams[s].elem_bytes;
+  }
+  if (streams[0].elem_bytes != (uint32_t)kb && ((uintptr_t)streams[0].ptr % kb) != 0)
+    return fail(B200SORT_EINVAL, "record array is not aligned to its key type");
+  if (((uintptr_t)streams[0].ptr % kb) != 0) return fail(B200SORT_EINVAL, "key array is not aligned to its key type");
+
+  const int cfg = pick_tile_cfg(kb, stage_bytes, di.smem_optin);
+  const TileCfg tc = kTileCfgs[cfg];
+  const int tile = tc.threads * tc.ipt;
+  const size_t smem = sweep_smem_bytes(tc, stage_bytes);
+  if (smem > di.smem_optin) return fail(B200SORT_ECUDA, "device offers %zu B of shared memory, %zu needed", di.smem_optin, smem);
+
+  Layout L;
+  make_layout(streams, n, std::min(tile, HYB_MIN_TILE), &L);
+  if (workspace == nullptr) {
+    if (int rc = cached_workspace(dev, L.total, &workspace)) return rc;
+  } else if (workspace_bytes < L.total) {
+    return fail(B200SORT_ENOMEM, "workspace of %zu bytes given, %zu needed", workspace_bytes, L.total);
+  } else if (((uintptr_t)workspace % 256) != 0) {
+    return fail(B200SORT_EINVAL, "workspace must be 256-byte aligned");
+  }
+  unsigned char *ws = (unsigned char *)workspace;
+  for (size_t s = 0; s < streams.size(); s++) ss.streams[s].buf[1] = ws + L.shadow_off[s];
+  uint64_t *ghist = (uint64_t *)(ws + L.ghist_off);
+  uint32_t *tile_counter = (uint32_t *)(ws + L.tilectr_off);
+  Plan *plan = (Plan *)(ws + L.plan_off);
+  uint64_t *bin_base = (uint64_t *)(ws + L.binbase_off);
+  uint64_t *lookback = (uint64_t *)(ws + L.lookback_off);
+
+  const uint64_t launches_before = g_launches.load();
+  CUDA_TRY(cudaMemsetAsync(ws + L.ctrl_off, 0, L.ctrl_bytes, stream));
+
+  const KeyOrder ko = make_key_order(key_type, ascending);
+
+  int algo = (int)opt_algo.load();
+  if (algo == 0) algo = (kb == 8 && n >= HYB_MIN_N) ? 2 : 1;
+  if (algo == 2 && kb != 8) algo = 1;
+
+  b200sort_stats stt{};
+  stt.num = n;
+  stt.record_bytes = rec_bytes;
+  stt.key_bytes = (uint32_t)kb;
+  stt.algo = (uint32_t)algo;
+
+  if (algo == 2) {
+    HybridJob hj{};
+    hj.ss = ss; hj.n = n; hj.ko = ko; hj.ws = ws; hj.ghist = ghist; hj.tile_counter = tile_counter; hj.plan = plan;
+    hj.bin_base = bin_base; hj.lookback = lookback; hj.ctrl = (HybridCtrl *)(ws + L.hyb_off);
+    hj.sm_count = di.sm_count; hj.smem_optin = di.smem_optin; hj.stage_bytes = stage_bytes; hj.stream = stream;
+    hj.cfg = cfg; hj.use_match = opt_use_match.load() != 0;
+    int rc = hybrid_sort_u64(hj, &stt);
+    if (rc != 0) return rc;
+  } else {
+    // ---- LSD: one histogram sweep over all digit positions, then one scatter pass per digit ----
+    HistArgs ha{};
+    ha.keys = ss.streams[0].buf[0];
+    ha.stride = streams[0].elem_bytes;
+    ha.n = n; ha.ko = ko; ha.first_digit = 0; ha.n_digits = kb; ha.ghist = ghist;
+    CUDA_TRY(launch_hist(kb, ha, di.sm_count, stream));
+
+    ScanArgs sa{};
+    sa.ghist = ghist; sa.bin_base = bin_base; sa.plan = plan; sa.n = n; sa.n_passes = kb;
+    for (int p = 0; p < kb; p++) sa.digit_of_pass[p] = p;
+    sa.allow_skip = (int)opt_allow_skip.load();
+    scan_kernel<<<1, RADIX, 0, stream>>>(sa);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+
+    const int64_t n_tiles = (n + tile - 1) / tile;
+    for (int p = 0; p < kb; p++) {
+      SweepArgs wa{};
+      wa.ss = ss; wa.n = n; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
+      wa.bin_base = bin_base + (size_t)p * RADIX;
+      wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
+      wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
+      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, smem, opt_use_match.load() != 0, stream));
+    }
+    CopyBackArgs ca{};
+    ca.ss = ss; ca.n = n; ca.plan = plan;
+    copyback_kernel<<<di.sm_count * 8, 256, 0, stream>>>(ca);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    stt.passes_planned = (uint32_t)kb;
+    stt.hist_sweeps = 1;
+    stt.algorithmic_bytes = (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
+  }
+  stt.kernel_launches = (uint32_t)(g_launches.load() - launches_before);
+  g_last_stats = stt;
+  g_have_stats = true;
+  return B200SORT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host/device dispatch
+// ------------------------------------------------------------------------------------------------
+enum Side { SIDE_HOST = 0, SIDE_DEVICE = 1 };
+
+static int side_of(const void *p, Side *out) {
+  cudaPointerAttributes at{};
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B200SORT_ECUDA, "cudaPointerGetAttributes failed: %s (no usable CUDA device? there is no CPU fallback)",
+                cudaGetErrorString(e));
+  }
+  *out = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? SIDE_DEVICE : SIDE_HOST;
+  return 0;
+}
+
+static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams, void *stream_v,
+                    void *workspace, size_t workspace_bytes) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B200SORT_ECUDA, "no CUDA device available (%s); libb200sort has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (n <= 1) return B200SORT_OK;  // src/radix_sort.hpp:276: nothing to do
+  Side side0;
+  if (int rc = side_of(streams[0].ptr, &side0)) return rc;
+  for (size_t s = 1; s < streams.size(); s++) {
+    Side sd;
+    if (int rc = side_of(streams[s].ptr, &sd)) return rc;
+    if (sd != side0) return fail(B200SORT_EINVAL, "arrays must be all in host memory or all in device memory");
+  }
+  if (side0 == SIDE_DEVICE) return sort_device(key_type, ascending, n, streams, stream, workspace, workspace_bytes);
+
+  // ---- host arrays: stage through device memory ---------------------------------------------------
+  std::vector<StreamDesc> dstreams(streams.size());
+  size_t total = 0;
+  std::vector<size_t> offs(streams.size());
+  for (size_t s = 0; s < streams.size(); s++) {
+    offs[s] = total;
+    total = align_up(total + (size_t)n * streams[s].elem_bytes, 256);
+  }
+  unsigned char *dbuf = nullptr;
+  e = cudaMalloc((void **)&dbuf, total);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B200SORT_ENOMEM, "cudaMalloc of %zu staging bytes failed: %s", total, cudaGetErrorString(e));
+  }
+  int rc = B200SORT_OK;
+  for (size_t s = 0; s < streams.size() && rc == 0; s++) {
+    dstreams[s] = {dbuf + offs[s], streams[s].elem_bytes};
+    e = cudaMemcpyAsync(dstreams[s].ptr, streams[s].ptr, (size_t)n * streams[s].elem_bytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) rc = fail(B200SORT_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == 0) rc = sort_device(key_type, ascending, n, dstreams, stream, workspace, workspace_bytes);
+  for (size_t s = 0; s < streams.size() && rc == 0; s++) {
+    e = cudaMemcpyAsync(streams[s].ptr, dstreams[s].ptr, (size_t)n * streams[s].elem_bytes, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) rc = fail(B200SORT_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  }
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess && rc == 0) rc = fail(B200SORT_ECUDA, "sort failed on the device: %s", cudaGetErrorString(e));
+  cudaFree(dbuf);
+  return rc;
+}
+
+static int check_soa(void *keys, int key_type, int64_t num, int n_payloads, void *const *payloads,
+                     const uint32_t *payload_elem_bytes, std::vector<StreamDesc> *out) {
+  const int kb = key_bytes_of(key_type);
+  if (kb == 0) return fail(B200SORT_EINVAL, "unknown key type %d", key_type);
+  if (num < 0) return fail(B200SORT_EINVAL, "negative element count");
+  if (n_payloads < 0 || n_payloads > MAX_STREAMS - 1)
+    return fail(B200SORT_ESHAPE, "%d payload streams (0..%d supported)", n_payloads, MAX_STREAMS - 1);
+  if (num > 1 && keys == nullptr) return fail(B200SORT_EINVAL, "keys is NULL");
+  out->push_back({keys, (uint32_t)kb});
+  for (int p = 0; p < n_payloads; p++) {
+    const uint32_t eb = payload_elem_bytes ? payload_elem_bytes[p] : 0;
+    if (eb < 1 || eb > 64) return fail(B200SORT_ESHAPE, "payload %d has element size %u (1..64 supported)", p, eb);
+    if (num > 1 && (payloads == nullptr || payloads[p] == nullptr)) return fail(B200SORT_EINVAL, "payload %d is NULL", p);
+    out->push_back({payloads ? payloads[p] : nullptr, eb});
+  }
+  return 0;
+}
+
+static int check_aos(void *records, int key_type, uint32_t record_bytes, int64_t num, std::vector<StreamDesc> *out) {
+  const int kb = key_bytes_of(key_type);
+  if (kb == 0) return fail(B200SORT_EINVAL, "unknown key type %d", key_type);
+  if (num < 0) return fail(B200SORT_EINVAL, "negative element count");
+  if (record_bytes < (uint32_t)kb || record_bytes > 64 || (record_bytes & (record_bytes - 1)) != 0)
+    return fail(B200SORT_ERECORD, "record size %u is not a power of two in [%d, 64]", record_bytes, kb);
+  if (num > 1 && records == nullptr) return fail(B200SORT_EINVAL, "records is NULL");
+  out->push_back({records, record_bytes});
+  return 0;
+}
+
+}  // namespace b200sort
+
+using namespace b200sort;
+
+extern "C" {
+
+int b200sort_sort_soa_ex(void *keys, int key_type, int64_t num, int ascending, int n_payloads, void *const *payloads,
+                         const uint32_t *payload_elem_bytes, int64_t cmp_sort_threshold, int cmp_sorter, void *stream,
+                         void *workspace, size_t workspace_bytes) {
+  if (cmp_sorter != B200SORT_CMP_INSERTION && cmp_sorter != B200SORT_CMP_NONE)
+    return fail(B200SORT_EINVAL, "unknown cmp_sorter %d", cmp_sorter);
+  (void)cmp_sort_threshold;  // a full sort satisfies the partial-sort contract of every threshold
+  std::vector<StreamDesc> streams;
+  if (int rc = check_soa(keys, key_type, num, n_payloads, payloads, payload_elem_bytes, &streams)) return rc;
+  return sort_any(key_type, ascending != 0, num, streams, stream, workspace, workspace_bytes);
+}
+
+int b200sort_sort_aos_ex(void *records, int key_type, uint32_t record_bytes, int64_t num, int ascending,
+                         int64_t cmp_sort_threshold, int cmp_sorter, void *stream, void *workspace,
+                         size_t workspace_bytes) {
+  if (cmp_sorter != B200SORT_CMP_INSERTION && cmp_sorter != B200SORT_CMP_NONE)
+    return fail(B200SORT_EINVAL, "unknown cmp_sorter %d", cmp_sorter);
+  (void)cmp_sort_threshold;
+  std::vector<StreamDesc> streams;
+  if (int rc = check_aos(records, key_type, record_bytes, num, &streams)) return rc;
+  return sort_any(key_type, ascending != 0, num, streams, stream, workspace, workspace_bytes);
+}
+
+int b200sort_sort_soa(void *keys, int key_type, int64_t num, int ascending, int n_payloads, void *const *payloads,
+                      const uint32_t *payload_elem_bytes, void *stream, void *workspace, size_t workspace_bytes) {
+  return b200sort_sort_soa_ex(keys, key_type, num, ascending, n_payloads, payloads, payload_elem_bytes, 16,
+                              B200SORT_CMP_INSERTION, stream, workspace, workspace_bytes);
+}
+
+int b200sort_sort_aos(void *records, int key_type, uint32_t record_bytes, int64_t num, int ascending, void *stream,
+                      void *workspace, size_t workspace_bytes) {
+  return b200sort_sort_aos_ex(records, key_type, record_bytes, num, ascending, 16, B200SORT_CMP_INSERTION, stream,
+                              workspace, workspace_bytes);
+}
+
+size_t b200sort_workspace_bytes(int key_type, int64_t num, int n_payloads, const uint32_t *payload_elem_bytes,
+                                uint32_t record_bytes) {
+  const int kb = key_bytes_of(key_type);
+  if (kb == 0 || num < 0) return 0;
+  std::vector<StreamDesc> streams;
+  if (record_bytes) {
+    streams.push_back({nullptr, record_bytes});
+  } else {
+    streams.push_back({nullptr, (uint32_t)kb});
+    for (int p = 0; p < n_payloads; p++) streams.push_back({nullptr, payload_elem_bytes[p]});
+  }
+  Layout L;
+  // the smallest tile any geometry uses bounds the look-back size from above
+  make_layout(streams, std::max<int64_t>(num, 1), HYB_MIN_TILE, &L);
+  return L.total;
+}
+
+const char *b200sort_last_error(void) { return g_last_error.c_str(); }
+int b200sort_version(void) { return B200SORT_VERSION; }
+uint64_t b200sort_launch_count(void) { return g_launches.load(); }
+
+static std::atomic<int64_t> *find_opt(const char *name) {
+  if (!name) return nullptr;
+  if (!strcmp(name, "algo")) return &opt_algo;
+  if (!strcmp(name, "tile_cfg")) return &opt_tile_cfg;
+  if (!strcmp(name, "use_match")) return &opt_use_match;
+  if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
+  if (!strcmp(name, "hist_match")) return &opt_hist_match;
+  return nullptr;
+}
+int b200sort_set_option(const char *name, int64_t value) {
+  auto *o = find_opt(name);
+  if (!o) return fail(B200SORT_EINVAL, "unknown option '%s'", name ? name : "(null)");
+  o->store(value);
+  return 0;
+}
+int64_t b200sort_get_option(const char *name) {
+  auto *o = find_opt(name);
+  return o ? o->load() : INT64_MIN;
+}
+
+int b200sort_last_stats(b200sort_stats *out) {
+  if (!out || !g_have_stats) return B200SORT_EINVAL;
+  *out = g_last_stats;
+  return 0;
+}
+
+void b200sort_release_cache(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto &kv : g_cache) {
+    if (kv.second.ptr) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(kv.first);
+      cudaDeviceSynchronize();
+      cudaFree(kv.second.ptr);
+      cudaSetDevice(cur);
+    }
+  }
+  g_cache.clear();
+}
+
+}  // extern "C"
+
+#include "mgpu.cuh"

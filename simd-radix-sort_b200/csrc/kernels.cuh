@@ -1,0 +1,494 @@
+// kernels.cuh -- sm_100a kernels of the digit pass (histogram, bucket-offset scan, one-sweep scatter).
+//
+// What they replace in the reference (paths under /root/reference):
+//   hist_kernel      <- getSortMasks + kpopcnt          src/radix_sort.hpp:225-240, :152  (per-vector 1-bit count)
+//   scan_kernel      <- writePosLeft/Right cursors       src/radix_sort.hpp:134-135,174-175 (2-bucket running prefix)
+//   onesweep_kernel  <- compress_store_left_right        src/radix_sort.hpp:242-267 (the permutation of keys and
+//                       + the look-back chain              every payload stream / the AoS record)
+// The reference partitions by ONE key bit per pass; here a pass partitions by an 8-bit digit of the
+// order-mapped key (to_ordered(), the closed form of bitDirUp, src/radix_sort.hpp:51-64).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200sort {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_STREAMS = 64;   // key stream + 63 payload streams (src/test.cpp:124-137 uses 63)
+constexpr int MAX_PASSES = 16;
+
+// ------------------------------------------------------------------------------------------------
+// key order
+// ------------------------------------------------------------------------------------------------
+template <int KB> struct UIntOf;
+template <> struct UIntOf<1> { using type = uint8_t; };
+template <> struct UIntOf<2> { using type = uint16_t; };
+template <> struct UIntOf<4> { using type = uint32_t; };
+template <> struct UIntOf<8> { using type = uint64_t; };
+template <int KB> struct OrdOf { using type = uint32_t; };
+template <> struct OrdOf<8> { using type = uint64_t; };
+
+// Maps raw key bits to an unsigned integer whose ascending order is the order the reference produces
+// (bitDirUp, src/radix_sort.hpp:51-64; table in bachelors-thesis.tex:1100-1113):
+//   unsigned: u = k; signed: u = k ^ SIGN; IEEE: u = (k & SIGN) ? ~k : k ^ SIGN; descending: ~u.
+// Encoded as two xor constants so that the kernels stay type-agnostic:
+//   u = k ^ xor_const ^ (sign(k) ? neg_xor : 0)
+struct KeyOrder {
+  uint64_t xor_const;  // SIGN for signed/float, ^ MASK when descending
+  uint64_t neg_xor;    // MASK ^ SIGN for float keys, else 0
+};
+
+template <int KB>
+__device__ __forceinline__ typename OrdOf<KB>::type to_ordered(typename UIntOf<KB>::type raw, const KeyOrder &ko) {
+  using O = typename OrdOf<KB>::type;
+  O u = (O)raw;
+  const O neg = (O)0 - ((u >> (8 * KB - 1)) & 1);  // all ones when the sign bit is set
+  return u ^ (O)ko.xor_const ^ (neg & (O)ko.neg_xor);
+}
+
+template <int KB>
+__device__ __forceinline__ typename UIntOf<KB>::type load_key(const unsigned char *base, int64_t i, uint32_t stride) {
+  return *reinterpret_cast<const typename UIntOf<KB>::type *>(base + (size_t)i * stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared descriptors
+// ------------------------------------------------------------------------------------------------
+struct Stream {
+  unsigned char *buf[2];    // [0] caller's array, [1] shadow copy in the workspace
+  uint32_t chunk_bytes;     // 1,2,4,8,16: granularity the stream is moved in
+  uint32_t chunks_per_elem; // element bytes / chunk_bytes
+};
+
+struct StreamSet {
+  int n_streams;            // streams[0] carries the key at byte offset 0 of each element
+  int pad;
+  Stream streams[MAX_STREAMS];
+};
+
+// written by scan_kernel, read by every later kernel of the same sort: which passes run, and from
+// which side of the ping-pong they read.
+struct Plan {
+  uint32_t skip[MAX_PASSES];
+  uint32_t src_sel[MAX_PASSES];
+  uint32_t final_sel;   // side that holds the result after the last executed pass
+  uint32_t n_exec;
+};
+
+// look-back status word: [63:62] flag, [61:57] generation tag, [56:0] value
+constexpr uint64_t LB_FLAG_AGG = 1ull << 62;
+constexpr uint64_t LB_FLAG_PREFIX = 2ull << 62;
+constexpr uint64_t LB_FLAG_MASK = 3ull << 62;
+constexpr int LB_TAG_SHIFT = 57;
+constexpr uint64_t LB_TAG_MASK = 31ull << LB_TAG_SHIFT;
+constexpr uint64_t LB_VALUE_MASK = (1ull << LB_TAG_SHIFT) - 1;
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// peers of this lane = lanes of the (full) warp holding the same digit
+template <bool USE_MATCH>
+__device__ __forceinline__ unsigned digit_peers(uint32_t d) {
+  if constexpr (USE_MATCH) {
+    return __match_any_sync(0xffffffffu, d);
+  } else {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; b++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
+      peers &= ((d >> b) & 1) ? bal : ~bal;
+    }
+    return peers;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: digit histograms of every digit position in one sweep over the keys.
+// Warp-aggregated shared-memory counters: lanes holding the same digit elect one lane that adds the
+// group's population (__match_any_sync), so a skewed digit costs one atomic per warp, not 32.
+// ------------------------------------------------------------------------------------------------
+struct HistArgs {
+  const unsigned char *keys;
+  uint32_t stride;      // bytes between consecutive keys (element size of stream 0)
+  int64_t n;
+  KeyOrder ko;
+  int first_digit;      // digit positions [first_digit, first_digit + n_digits) are counted
+  int n_digits;
+  uint64_t *ghist;      // [KB][RADIX] counters, zeroed by the host
+};
+
+template <int KB, int THREADS, int IPT, bool USE_MATCH>
+__global__ void __launch_bounds__(THREADS) hist_kernel(HistArgs a) {
+  using O = typename OrdOf<KB>::type;
+  __shared__ uint32_t sh[KB * RADIX];
+  for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) sh[i] = 0;
+  __syncthreads();
+
+  constexpr int TILE = THREADS * IPT;
+  const int64_t n_tiles = (a.n + TILE - 1) / TILE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * TILE;
+    O u[IPT];
+    bool valid[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const int64_t i = base + (int64_t)r * THREADS + threadIdx.x;
+      valid[r] = i < a.n;
+      u[r] = valid[r] ? to_ordered<KB>(load_key<KB>(a.keys, i, a.stride), a.ko) : (O)0;
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid[r]);
+      if (valid[r]) {
+        for (int p = a.first_digit; p < a.first_digit + a.n_digits; p++) {
+          const uint32_t d = (uint32_t)(u[r] >> (p * RADIX_BITS)) & (RADIX - 1);
+          if constexpr (USE_MATCH) {
+            const unsigned peers = __match_any_sync(vmask, d);
+            if ((peers & lanemask_lt()) == 0) atomicAdd(&sh[p * RADIX + d], (uint32_t)__popc(peers));
+          } else {
+            atomicAdd(&sh[p * RADIX + d], 1u);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ghist[i]), (unsigned long long)c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: per-pass exclusive scan of the 256 bucket counts -> bucket offsets, plus the pass plan
+// (a digit position on which every key agrees is skipped: the early-out the reference lacks,
+// bachelors-thesis.tex:4156-4176).  One block of RADIX threads.
+// ------------------------------------------------------------------------------------------------
+struct ScanArgs {
+  const uint64_t *ghist;   // [n_passes][RADIX], indexed by digit position
+  uint64_t *bin_base;      // [n_passes][RADIX] out
+  Plan *plan;
+  int64_t n;
+  int n_passes;            // passes 0..n_passes-1 in execution order
+  int digit_of_pass[MAX_PASSES];
+  int allow_skip;
+};
+
+__global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
+  __shared__ uint64_t warp_sum[RADIX / 32];
+  __shared__ uint32_t s_skip[MAX_PASSES];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t < MAX_PASSES) s_skip[t] = 0;
+  __syncthreads();
+  for (int p = 0; p < a.n_passes; p++) {
+    const int dp = a.digit_of_pass[p];
+    const uint64_t c = a.ghist[dp * RADIX + t];
+    if (a.allow_skip && c == (uint64_t)a.n) s_skip[p] = 1;
+    uint64_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_sum[w] = inc;
+    __syncthreads();
+    uint64_t off = 0;
+    for (int i = 0; i < w; i++) off += warp_sum[i];
+    a.bin_base[p * RADIX + t] = off + inc - c;
+    __syncthreads();
+  }
+  if (t == 0) {
+    uint32_t sel = 0, n_exec = 0;
+    for (int p = 0; p < a.n_passes; p++) {
+      a.plan->skip[p] = s_skip[p];
+      a.plan->src_sel[p] = sel;
+      if (!s_skip[p]) { sel ^= 1; n_exec++; }
+    }
+    a.plan->final_sel = sel;
+    a.plan->n_exec = n_exec;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one-sweep scatter of one digit pass.
+//  - a CTA takes the next tile (atomic ticket), ranks its keys by digit in shared memory (warp-private
+//    counters + peer masks: stable), publishes the tile's per-digit counts, and resolves its global
+//    bucket offsets with a decoupled look-back over the preceding tiles' status words (K2b: the
+//    exclusive scan across tiles never becomes a separate pass);
+//  - keys, then every payload stream (or every 16-byte column of the AoS record), are staged in shared
+//    memory in bucket order and written out with consecutive threads writing consecutive addresses of
+//    each bucket.
+// ------------------------------------------------------------------------------------------------
+struct SweepArgs {
+  StreamSet ss;
+  int64_t n;
+  KeyOrder ko;
+  int pass;                // index into plan / bin_base / tile_counter
+  int shift;               // bit offset of this pass's digit in the ordered key
+  const uint64_t *bin_base;  // [RADIX] for this pass
+  uint64_t *lookback;      // [n_tiles][RADIX]
+  uint32_t *tile_counter;  // one per pass
+  const Plan *plan;
+  uint32_t tag;            // generation tag of this pass's status words (1..31)
+  uint32_t stage_bytes;    // bytes per staged chunk (max chunk size over streams)
+  // multi-GPU partition pass: when lut != nullptr the "digit" is the destination rank looked up from the
+  // top lut_bits bits of the ordered key (lut has 2^lut_bits entries), not a radix digit
+  const uint8_t *lut;
+  int lut_shift;
+};
+
+template <int KB>
+__device__ __forceinline__ uint32_t pass_digit(typename UIntOf<KB>::type raw, const SweepArgs &a) {
+  const typename OrdOf<KB>::type u = to_ordered<KB>(raw, a.ko);
+  if (a.lut != nullptr) return a.lut[(uint32_t)(u >> a.lut_shift)];
+  return (uint32_t)(u >> a.shift) & (RADIX - 1);
+}
+
+template <typename T, int THREADS, int IPT>
+__device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
+                                            const uint8_t *sdigit, const int64_t *gbase, const uint16_t *srank,
+                                            int64_t tile_base, int n_valid, uint32_t cpe, uint32_t c, int warp,
+                                            int lane) {
+  T *stage = reinterpret_cast<T *>(stage_raw);
+  const T *s = reinterpret_cast<const T *>(src);
+  T *d = reinterpret_cast<T *>(dst);
+  // loads are issued in batches of up to 8 chunks (4 for 16-byte chunks) per thread to bound register use
+  constexpr int BATCH_MAX = sizeof(T) == 16 ? 4 : 8;
+  constexpr int BATCH = BATCH_MAX < IPT ? BATCH_MAX : IPT;
+  static_assert(IPT % BATCH == 0, "IPT must be a multiple of the load batch");
+#pragma unroll 1
+  for (int r0 = 0; r0 < IPT; r0 += BATCH) {
+    T v[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) {
+      const int idx = warp * (IPT * 32) + (r0 + b) * 32 + lane;
+      if (idx < n_valid) v[b] = s[(size_t)(tile_base + idx) * cpe + c];
+    }
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) {
+      const int idx = warp * (IPT * 32) + (r0 + b) * 32 + lane;
+      if (idx < n_valid) stage[srank[idx]] = v[b];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_valid; i += THREADS) {
+    const int64_t g = gbase[sdigit[i]] + i;
+    d[(size_t)g * cpe + c] = stage[i];
+  }
+}
+
+// ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
+// ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
+// ~130 registers per thread instead of 64-98, so the narrow widths get their own instantiation.
+template <int KB, int THREADS, int IPT, bool USE_MATCH, bool ANYCHUNK>
+__global__ void __launch_bounds__(THREADS) onesweep_kernel(const __grid_constant__ SweepArgs a) {
+  static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
+  constexpr int TILE = THREADS * IPT;
+  constexpr int NWARPS = THREADS / 32;
+  using KeyT = typename UIntOf<KB>::type;
+  using O = typename OrdOf<KB>::type;
+
+  if (a.plan->skip[a.pass]) return;
+  const uint32_t sel = a.plan->src_sel[a.pass];
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char *stage = smem;                                            // TILE * stage_bytes
+  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)TILE * a.stage_bytes);  // NWARPS*RADIX
+  int64_t *gbase = reinterpret_cast<int64_t *>(warp_cnt + NWARPS * RADIX);                  // RADIX
+  uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase + RADIX);                         // RADIX
+  uint32_t *s_wsum = s_prefix + RADIX;                                                       // 32
+  uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
+  uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) s_wsum[31] = atomicAdd(&a.tile_counter[a.pass], 1u);
+  for (int i = tid; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
+  __syncthreads();
+  const int64_t tile = s_wsum[31];
+  const int64_t tile_base = tile * TILE;
+  const int64_t remaining = a.n - tile_base;
+  const int n_valid = remaining < TILE ? (int)remaining : TILE;
+
+  const Stream &ks = a.ss.streams[0];
+  const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
+  const unsigned char *ksrc = ks.buf[sel];
+
+  // ---- load + rank -------------------------------------------------------------------------------
+  KeyT raw[IPT];
+  uint32_t rank[IPT];
+#pragma unroll
+  for (int r = 0; r < IPT; r++) {
+    const int idx = warp * (IPT * 32) + r * 32 + lane;
+    raw[r] = idx < n_valid ? load_key<KB>(ksrc, tile_base + idx, key_stride) : (KeyT)0;
+  }
+#pragma unroll
+  for (int r = 0; r < IPT; r++) {
+    const int idx = warp * (IPT * 32) + r * 32 + lane;
+    // padding of the last tile ranks behind everything (digit 255, last in index order)
+    const uint32_t d = idx < n_valid ? pass_digit<KB>(raw[r], a) : (RADIX - 1);
+    const unsigned peers = digit_peers<USE_MATCH>(d);
+    uint32_t *c = &warp_cnt[warp * RADIX + d];
+    const uint32_t cnt = *c;
+    __syncwarp();
+    const uint32_t lower = __popc(peers & lanemask_lt());
+    rank[r] = cnt + lower;
+    if (lower == 0) *c = cnt + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per-digit totals: exclusive scan across warps, then across digits ----------------------------
+  uint32_t my_count = 0;
+  if (tid < RADIX) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; w++) {
+      const uint32_t t = warp_cnt[w * RADIX + tid];
+      warp_cnt[w * RADIX + tid] = run;
+      run += t;
+    }
+    my_count = run;
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    s_prefix[tid] = inc - run;  // exclusive within the warp's 32 digits; warp offset added below
+  }
+  __syncthreads();
+  const uint64_t tagbits = (uint64_t)a.tag << LB_TAG_SHIFT;
+  uint64_t valid_count = 0;
+  if (tid < RADIX) {
+    uint32_t off = 0;
+    for (int w = 0; w < warp; w++) off += s_wsum[w];
+    s_prefix[tid] += off;
+    // counts published to other tiles exclude the padding of the last tile
+    valid_count = my_count - ((tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
+    uint64_t *slot = &a.lookback[(size_t)tile * RADIX + tid];
+    if (tile == 0)
+      st_relaxed_u64(slot, LB_FLAG_PREFIX | tagbits | (a.bin_base[tid] + valid_count));
+    else
+      st_relaxed_u64(slot, LB_FLAG_AGG | tagbits | valid_count);
+  }
+  __syncthreads();  // s_prefix complete
+
+  // ---- decoupled look-back (one thread per digit) while the other warps stage the keys --------------
+  if (tid < RADIX) {
+    uint64_t excl;
+    if (tile == 0) {
+      excl = a.bin_base[tid];
+    } else {
+      excl = 0;
+      int64_t t = tile - 1;
+      while (true) {
+        const uint64_t w = ld_relaxed_u64(&a.lookback[(size_t)t * RADIX + tid]);
+        if ((w & LB_TAG_MASK) != tagbits || (w & LB_FLAG_MASK) == 0) continue;  // not published yet
+        excl += w & LB_VALUE_MASK;
+        if ((w & LB_FLAG_MASK) == LB_FLAG_PREFIX) break;
+        t--;
+      }
+      st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
+    }
+    gbase[tid] = (int64_t)excl - (int64_t)s_prefix[tid];
+  }
+
+  // final rank inside the tile = digit offset + offset of this warp inside the digit + rank inside warp
+#pragma unroll
+  for (int r = 0; r < IPT; r++) {
+    const int idx = warp * (IPT * 32) + r * 32 + lane;
+    const uint32_t d = idx < n_valid ? pass_digit<KB>(raw[r], a) : (RADIX - 1);
+    rank[r] += s_prefix[d] + warp_cnt[warp * RADIX + d];
+    sdigit[rank[r]] = (uint8_t)d;
+    srank[idx] = (uint16_t)rank[r];  // payload streams pick their slot up from here
+  }
+
+  // ---- move every stream ---------------------------------------------------------------------------
+  int first_stream = 0;
+  if (key_stride == KB) {
+    // SoA: the keys are already in registers
+    KeyT *kst = reinterpret_cast<KeyT *>(stage);
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const int idx = warp * (IPT * 32) + r * 32 + lane;
+      if (idx < n_valid) kst[rank[r]] = raw[r];
+    }
+    __syncthreads();
+    KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
+    for (int i = tid; i < n_valid; i += THREADS) kdst[gbase[sdigit[i]] + i] = kst[i];
+    first_stream = 1;
+  } else {
+    __syncthreads();  // sdigit / gbase visible
+  }
+  for (int s = first_stream; s < a.ss.n_streams; s++) {
+    const Stream &st = a.ss.streams[s];
+    const unsigned char *src = st.buf[sel];
+    unsigned char *dst = st.buf[sel ^ 1];
+    for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
+      __syncthreads();  // previous use of the staging buffer is over
+      const uint32_t cb = st.chunk_bytes;
+      if (cb == 8) move_chunks<uint64_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      else if (cb == 4) move_chunks<uint32_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      else if (cb == 16) move_chunks<uint4, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      else if constexpr (ANYCHUNK) {
+        if (cb == 2) move_chunks<uint16_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+        else move_chunks<uint8_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// copy the result back into the caller's arrays when the last executed pass left it in the shadow
+// ------------------------------------------------------------------------------------------------
+struct CopyBackArgs {
+  StreamSet ss;
+  int64_t n;
+  const Plan *plan;
+};
+
+__global__ void __launch_bounds__(256) copyback_kernel(const __grid_constant__ CopyBackArgs a) {
+  if (a.plan->final_sel == 0) return;
+  for (int s = 0; s < a.ss.n_streams; s++) {
+    const Stream &st = a.ss.streams[s];
+    const size_t bytes = (size_t)a.n * st.chunk_bytes * st.chunks_per_elem;
+    const unsigned char *src = st.buf[1];
+    unsigned char *dst = st.buf[0];
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t gsz = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      const size_t nv = bytes / 16;
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+      uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+      for (size_t i = gtid; i < nv; i += gsz) d4[i] = s4[i];
+      for (size_t i = nv * 16 + gtid; i < bytes; i += gsz) dst[i] = src[i];
+    } else {
+      // rare: caller array not 16-byte aligned; move in the stream's own chunk size
+      const size_t nc = bytes / st.chunk_bytes;
+      switch (st.chunk_bytes) {
+        case 1: for (size_t i = gtid; i < nc; i += gsz) dst[i] = src[i]; break;
+        case 2: for (size_t i = gtid; i < nc; i += gsz) ((uint16_t *)dst)[i] = ((const uint16_t *)src)[i]; break;
+        case 4: for (size_t i = gtid; i < nc; i += gsz) ((uint32_t *)dst)[i] = ((const uint32_t *)src)[i]; break;
+        case 8: for (size_t i = gtid; i < nc; i += gsz) ((uint64_t *)dst)[i] = ((const uint64_t *)src)[i]; break;
+        default: for (size_t i = gtid; i < nc; i += gsz) ((uint4 *)dst)[i] = ((const uint4 *)src)[i]; break;
+      }
+    }
+  }
+}
+
+}  // namespace b200sort
