@@ -102,7 +102,7 @@ uint64_t b200sort_launch_count(void);
 
 /* Tuning/ablation knobs, process-wide.  Known names: "algo" (0 auto, 1 LSD one-sweep passes,
  * 2 hybrid MSB), "tile_cfg" (index of the scatter tile geometry), "use_match" (1 = __match_any_sync
- * ranking, 0 = ballot ranking).  Returns 0, or B200SORT_EINVAL for an unknown name. */
+ * ranking, 0 = ballot ranking), "hist_match", "allow_skip", "profile".  Returns 0, or B200SORT_EINVAL for an unknown name. */
 int b200sort_set_option(const char *name, int64_t value);
 int64_t b200sort_get_option(const char *name);
 
@@ -118,6 +118,11 @@ typedef struct b200sort_stats {
   uint64_t algorithmic_bytes; /* H*N*K + P*2*N*R with the planned pass counts */
 } b200sort_stats;
 int b200sort_last_stats(b200sort_stats *out);
+
+/* Per-kernel device times of the last sort on this thread, recorded with CUDA events on the sort's
+ * stream when option "profile" is 1.  kinds[i]: 0 histogram, 1 scan, 2 scatter pass, 3 copy-back,
+ * 4 segment finish, 5 other.  Returns the number of entries written (<= capacity) or a negative code. */
+int b200sort_last_profile(int *kinds, float *ms, int capacity);
 
 /* Releases the per-device workspace caches held by the library. */
 void b200sort_release_cache(void);

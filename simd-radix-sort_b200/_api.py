@@ -63,6 +63,8 @@ def lib():
         L.b200sort_last_stats.argtypes = [ctypes.POINTER(_Stats)]
         L.b200sort_last_stats.restype = i32
         L.b200sort_release_cache.restype = None
+        L.b200sort_last_profile.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float), i32]
+        L.b200sort_last_profile.restype = i32
         L.b200sort_mgpu_unique_id.argtypes = [vp]
         L.b200sort_mgpu_unique_id.restype = i32
         L.b200sort_mgpu_comm_create.argtypes = [vpp, i32, i32, vp]
@@ -102,6 +104,19 @@ def last_stats() -> dict:
     s = _Stats()
     _check(lib().b200sort_last_stats(ctypes.byref(s)))
     return {f: getattr(s, f) for f, _ in _Stats._fields_}
+
+
+PROFILE_KINDS = ["hist", "scan", "sweep", "copyback", "segfix", "other"]
+
+
+def last_profile():
+    """[(kernel kind, milliseconds)] of the last sort on this thread (needs set_option("profile", 1))."""
+    kinds = (ctypes.c_int * 256)()
+    ms = (ctypes.c_float * 256)()
+    n = lib().b200sort_last_profile(kinds, ms, 256)
+    if n < 0:
+        _check(n)
+    return [(PROFILE_KINDS[kinds[i]], float(ms[i])) for i in range(n)]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -52,5 +52,22 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+BENCH = PKG / "sortbench"
+
+
+def build_sortbench(force: bool = False) -> Path:
+    """The native self-check / micro-benchmark driver (a development tool)."""
+    src = CSRC / "sortbench.cu"
+    if not force and BENCH.exists() and BENCH.stat().st_mtime > max(src.stat().st_mtime, LIB.stat().st_mtime):
+        return BENCH
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-o", str(BENCH),
+           str(src), "-L", str(PKG), "-lb200sort", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+    return BENCH
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
+    print(build_sortbench(force="--force" in sys.argv))

@@ -37,6 +37,29 @@ static std::atomic<int64_t> opt_use_match{1};
 static std::atomic<int64_t> opt_allow_skip{1};
 static std::atomic<int64_t> opt_hist_match{1};
 
+// optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
+enum ProfKind { PK_HIST = 0, PK_SCAN = 1, PK_SWEEP = 2, PK_COPYBACK = 3, PK_SEGFIX = 4, PK_OTHER = 5 };
+struct ProfEntry { int kind; cudaEvent_t e0, e1; };
+static std::atomic<int64_t> opt_profile{0};
+static thread_local std::vector<ProfEntry> g_prof;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
+
+static void prof_reset() {
+  for (auto &p : g_prof) { g_prof_pool.push_back(p.e0); g_prof_pool.push_back(p.e1); }
+  g_prof.clear();
+}
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+  bool on; ProfEntry pe; cudaStream_t st;
+  ProfScope(int kind, cudaStream_t s) : on(opt_profile.load() != 0), st(s) {
+    if (on) { pe.kind = kind; pe.e0 = prof_event(); pe.e1 = prof_event(); cudaEventRecord(pe.e0, st); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(pe.e1, st); g_prof.push_back(pe); } }
+};
+
 static int fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -84,7 +107,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
 struct TileCfg { int threads, ipt; };
-static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 32}};
+static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 8}};
 static constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 
 static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes) {
@@ -92,16 +115,17 @@ static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes) {
   return tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3;
 }
 
-template <int KB, int THREADS, int IPT>
+template <int KB, int THREADS, int IPT, int MINB>
 static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match, cudaStream_t st) {
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   for (int s = (a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == KB) ? 1 : 0; s < a.ss.n_streams; s++)
     any = any || a.ss.streams[s].chunk_bytes < 4;
   void (*k)(const SweepArgs);
-  if (any) k = use_match ? onesweep_kernel<KB, THREADS, IPT, true, true> : onesweep_kernel<KB, THREADS, IPT, false, true>;
-  else k = use_match ? onesweep_kernel<KB, THREADS, IPT, true, false> : onesweep_kernel<KB, THREADS, IPT, false, false>;
+  if (any) k = use_match ? onesweep_kernel<KB, THREADS, IPT, MINB, true, true> : onesweep_kernel<KB, THREADS, IPT, MINB, false, true>;
+  else k = use_match ? onesweep_kernel<KB, THREADS, IPT, MINB, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, false, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  ProfScope ps(PK_SWEEP, st);
   k<<<(unsigned)n_tiles, THREADS, smem, st>>>(a);
   g_launches++;
   return cudaGetLastError();
@@ -111,10 +135,10 @@ template <int KB>
 static cudaError_t launch_sweep_kb(int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match,
                                    cudaStream_t st) {
   switch (cfg) {
-    case 0: return launch_sweep_t<KB, 512, 16>(a, n_tiles, smem, use_match, st);
-    case 1: return launch_sweep_t<KB, 256, 16>(a, n_tiles, smem, use_match, st);
-    case 2: return launch_sweep_t<KB, 512, 8>(a, n_tiles, smem, use_match, st);
-    default: return launch_sweep_t<KB, 256, 32>(a, n_tiles, smem, use_match, st);
+    case 0: return launch_sweep_t<KB, 512, 16, 1>(a, n_tiles, smem, use_match, st);
+    case 1: return launch_sweep_t<KB, 256, 16, 3>(a, n_tiles, smem, use_match, st);
+    case 2: return launch_sweep_t<KB, 512, 8, 2>(a, n_tiles, smem, use_match, st);
+    default: return launch_sweep_t<KB, 256, 8, 4>(a, n_tiles, smem, use_match, st);
   }
 }
 
@@ -132,6 +156,7 @@ constexpr int HIST_THREADS = 512, HIST_IPT = 8;
 
 template <int KB>
 static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, cudaStream_t st) {
+  ProfScope ps(PK_HIST, st);
   if (use_match)
     hist_kernel<KB, HIST_THREADS, HIST_IPT, true><<<grid, HIST_THREADS, 0, st>>>(a);
   else
@@ -294,6 +319,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   uint64_t *lookback = (uint64_t *)(ws + L.lookback_off);
 
   const uint64_t launches_before = g_launches.load();
+  prof_reset();
   CUDA_TRY(cudaMemsetAsync(ws + L.ctrl_off, 0, L.ctrl_bytes, stream));
 
   const KeyOrder ko = make_key_order(key_type, ascending);
@@ -328,7 +354,10 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     sa.ghist = ghist; sa.bin_base = bin_base; sa.plan = plan; sa.n = n; sa.n_passes = kb;
     for (int p = 0; p < kb; p++) sa.digit_of_pass[p] = p;
     sa.allow_skip = (int)opt_allow_skip.load();
-    scan_kernel<<<1, RADIX, 0, stream>>>(sa);
+    {
+      ProfScope ps(PK_SCAN, stream);
+      scan_kernel<<<1, RADIX, 0, stream>>>(sa);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 
@@ -343,7 +372,10 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     }
     CopyBackArgs ca{};
     ca.ss = ss; ca.n = n; ca.plan = plan;
-    copyback_kernel<<<di.sm_count * 8, 256, 0, stream>>>(ca);
+    {
+      ProfScope ps(PK_COPYBACK, stream);
+      copyback_kernel<<<di.sm_count * 8, 256, 0, stream>>>(ca);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     stt.passes_planned = (uint32_t)kb;
@@ -376,6 +408,7 @@ static int side_of(const void *p, Side *out) {
 static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams, void *stream_v,
                     void *workspace, size_t workspace_bytes) {
   cudaStream_t stream = (cudaStream_t)stream_v;
+  if (n <= 1) return B200SORT_OK;  // src/radix_sort.hpp:276: nothing to do for 0 or 1 element
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -383,7 +416,6 @@ static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<S
     return fail(B200SORT_ECUDA, "no CUDA device available (%s); libb200sort has no CPU fallback",
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   }
-  if (n <= 1) return B200SORT_OK;  // src/radix_sort.hpp:276: nothing to do
   Side side0;
   if (int rc = side_of(streams[0].ptr, &side0)) return rc;
   for (size_t s = 1; s < streams.size(); s++) {
@@ -521,6 +553,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "use_match")) return &opt_use_match;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
+  if (!strcmp(name, "profile")) return &opt_profile;
   return nullptr;
 }
 int b200sort_set_option(const char *name, int64_t value) {
@@ -538,6 +571,20 @@ int b200sort_last_stats(b200sort_stats *out) {
   if (!out || !g_have_stats) return B200SORT_EINVAL;
   *out = g_last_stats;
   return 0;
+}
+
+int b200sort_last_profile(int *kinds, float *ms, int capacity) {
+  int n = 0;
+  for (auto &p : g_prof) {
+    if (n >= capacity) break;
+    if (cudaEventSynchronize(p.e1) != cudaSuccess) return fail(B200SORT_ECUDA, "profile event failed");
+    float t = 0;
+    cudaEventElapsedTime(&t, p.e0, p.e1);
+    kinds[n] = p.kind;
+    ms[n] = t;
+    n++;
+  }
+  return n;
 }
 
 void b200sort_release_cache(void) {

@@ -250,21 +250,53 @@ struct SweepArgs {
   int lut_shift;
 };
 
-template <int KB>
-__device__ __forceinline__ uint32_t pass_digit(typename UIntOf<KB>::type raw, const SweepArgs &a) {
-  const typename OrdOf<KB>::type u = to_ordered<KB>(raw, a.ko);
-  if (a.lut != nullptr) return a.lut[(uint32_t)(u >> a.lut_shift)];
-  return (uint32_t)(u >> a.shift) & (RADIX - 1);
+// Per-pass constants that make the digit a handful of 32-bit operations: because the order mapping is
+// an xor, digit(ordered key) = digit(raw key) ^ digit(xor_const) ^ (negative ? digit(neg_xor) : 0).
+struct DigitX {
+  uint32_t hi_word;  // 1: the digit lies in bits 32..63 of an 8-byte key
+  uint32_t bit;      // shift inside that 32-bit word
+  uint32_t xc, nx;   // digit(xor_const), digit(neg_xor)
+};
+
+__device__ __forceinline__ DigitX make_digitx(const KeyOrder &ko, int shift) {
+  DigitX x;
+  x.hi_word = shift >= 32;
+  x.bit = shift & 31;
+  x.xc = (uint32_t)(ko.xor_const >> shift) & (RADIX - 1);
+  x.nx = (uint32_t)(ko.neg_xor >> shift) & (RADIX - 1);
+  return x;
 }
 
-template <typename T, int THREADS, int IPT>
+template <int KB>
+__device__ __forceinline__ uint32_t fast_digit(typename UIntOf<KB>::type raw, const DigitX &x) {
+  if constexpr (KB == 8) {
+    const uint32_t hi = (uint32_t)(raw >> 32), lo = (uint32_t)raw;
+    const uint32_t w = x.hi_word ? hi : lo;
+    const uint32_t neg = (uint32_t)((int32_t)hi >> 31);
+    return (((w >> x.bit) & (RADIX - 1)) ^ x.xc) ^ (neg & x.nx);
+  } else {
+    const uint32_t w = (uint32_t)raw;
+    const uint32_t neg = (uint32_t)((int32_t)(w << (32 - 8 * KB)) >> 31);
+    return (((w >> x.bit) & (RADIX - 1)) ^ x.xc) ^ (neg & x.nx);
+  }
+}
+
+template <int KB>
+__device__ __forceinline__ uint32_t lut_digit(typename UIntOf<KB>::type raw, const SweepArgs &a) {
+  return a.lut[(uint32_t)(to_ordered<KB>(raw, a.ko) >> a.lut_shift)];
+}
+
+// Moves one chunk column of one stream through the staging buffer.  goff[k] is the destination element
+// index of staged slot tid + k*THREADS (computed once per tile, shared by all streams).
+template <typename T, int THREADS, int IPT, bool FULL>
 __device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
-                                            const uint8_t *sdigit, const int64_t *gbase, const uint16_t *srank,
-                                            int64_t tile_base, int n_valid, uint32_t cpe, uint32_t c, int warp,
-                                            int lane) {
+                                            const uint16_t *srank, const int64_t (&goff)[IPT], int64_t tile_base,
+                                            int n_valid, uint32_t cpe, uint32_t c, int warp, int lane) {
   T *stage = reinterpret_cast<T *>(stage_raw);
-  const T *s = reinterpret_cast<const T *>(src);
-  T *d = reinterpret_cast<T *>(dst);
+  const int idx0 = warp * (IPT * 32) + lane;
+  const T *s = reinterpret_cast<const T *>(src) + ((size_t)(tile_base + idx0) * cpe + c);
+  T *d = reinterpret_cast<T *>(dst) + c;
+  const uint16_t *sr = srank + idx0;
   // loads are issued in batches of up to 8 chunks (4 for 16-byte chunks) per thread to bound register use
   constexpr int BATCH_MAX = sizeof(T) == 16 ? 4 : 8;
   constexpr int BATCH = BATCH_MAX < IPT ? BATCH_MAX : IPT;
@@ -273,80 +305,75 @@ __device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned c
   for (int r0 = 0; r0 < IPT; r0 += BATCH) {
     T v[BATCH];
 #pragma unroll
-    for (int b = 0; b < BATCH; b++) {
-      const int idx = warp * (IPT * 32) + (r0 + b) * 32 + lane;
-      if (idx < n_valid) v[b] = s[(size_t)(tile_base + idx) * cpe + c];
-    }
+    for (int b = 0; b < BATCH; b++)
+      if (FULL || idx0 + (r0 + b) * 32 < n_valid) v[b] = s[(size_t)((r0 + b) * 32) * cpe];
 #pragma unroll
-    for (int b = 0; b < BATCH; b++) {
-      const int idx = warp * (IPT * 32) + (r0 + b) * 32 + lane;
-      if (idx < n_valid) stage[srank[idx]] = v[b];
-    }
+    for (int b = 0; b < BATCH; b++)
+      if (FULL || idx0 + (r0 + b) * 32 < n_valid) stage[sr[(r0 + b) * 32]] = v[b];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_valid; i += THREADS) {
-    const int64_t g = gbase[sdigit[i]] + i;
-    d[(size_t)g * cpe + c] = stage[i];
+#pragma unroll
+  for (int k = 0; k < IPT; k++) {
+    const int i = threadIdx.x + k * THREADS;
+    if (FULL || i < n_valid) d[(size_t)goff[k] * cpe] = stage[i];
   }
 }
 
-// ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
-// ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
-// ~130 registers per thread instead of 64-98, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, bool USE_MATCH, bool ANYCHUNK>
-__global__ void __launch_bounds__(THREADS) onesweep_kernel(const __grid_constant__ SweepArgs a) {
-  static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
+template <int KB, int THREADS, int IPT, bool USE_MATCH, bool ANYCHUNK, bool FULL>
+__device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
+                                           const uint32_t sel) {
   constexpr int TILE = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
   using KeyT = typename UIntOf<KB>::type;
-  using O = typename OrdOf<KB>::type;
 
-  if (a.plan->skip[a.pass]) return;
-  const uint32_t sel = a.plan->src_sel[a.pass];
-
-  extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char *stage = smem;                                            // TILE * stage_bytes
-  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)TILE * a.stage_bytes);  // NWARPS*RADIX
-  int64_t *gbase = reinterpret_cast<int64_t *>(warp_cnt + NWARPS * RADIX);                  // RADIX
-  uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase + RADIX);                         // RADIX
-  uint32_t *s_wsum = s_prefix + RADIX;                                                       // 32
+  unsigned char *stage = smem;                                                               // TILE * stage_bytes
+  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)TILE * a.stage_bytes);   // NWARPS*RADIX
+  int64_t *gbase = reinterpret_cast<int64_t *>(warp_cnt + NWARPS * RADIX);                   // RADIX
+  uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase + RADIX);                          // RADIX
+  uint32_t *s_wsum = s_prefix + RADIX;                                                        // 32
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
   uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) s_wsum[31] = atomicAdd(&a.tile_counter[a.pass], 1u);
-  for (int i = tid; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
-  __syncthreads();
-  const int64_t tile = s_wsum[31];
   const int64_t tile_base = tile * TILE;
-  const int64_t remaining = a.n - tile_base;
-  const int n_valid = remaining < TILE ? (int)remaining : TILE;
+  const int idx0 = warp * (IPT * 32) + lane;  // this thread's items are idx0 + r*32
 
   const Stream &ks = a.ss.streams[0];
   const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
-  const unsigned char *ksrc = ks.buf[sel];
+  const unsigned char *kp = ks.buf[sel] + (size_t)(tile_base + idx0) * key_stride;
 
-  // ---- load + rank -------------------------------------------------------------------------------
+  // ---- load keys, digits ---------------------------------------------------------------------------
   KeyT raw[IPT];
-  uint32_t rank[IPT];
+  uint32_t dig[IPT];
 #pragma unroll
-  for (int r = 0; r < IPT; r++) {
-    const int idx = warp * (IPT * 32) + r * 32 + lane;
-    raw[r] = idx < n_valid ? load_key<KB>(ksrc, tile_base + idx, key_stride) : (KeyT)0;
+  for (int r = 0; r < IPT; r++)
+    raw[r] = (FULL || idx0 + r * 32 < n_valid) ? *reinterpret_cast<const KeyT *>(kp + (size_t)(r * 32) * key_stride) : (KeyT)0;
+  if (a.lut == nullptr) {
+    const DigitX dx = make_digitx(a.ko, a.shift);
+#pragma unroll
+    for (int r = 0; r < IPT; r++) dig[r] = fast_digit<KB>(raw[r], dx);
+  } else {
+#pragma unroll
+    for (int r = 0; r < IPT; r++) dig[r] = lut_digit<KB>(raw[r], a);
   }
+  if (!FULL) {
+    // padding of the last tile ranks behind everything (digit 255, last in index order)
+#pragma unroll
+    for (int r = 0; r < IPT; r++)
+      if (idx0 + r * 32 >= n_valid) dig[r] = RADIX - 1;
+  }
+
+  // ---- rank inside the warp (stable) -----------------------------------------------------------------
+  uint32_t rank[IPT];
+  uint32_t *wc = warp_cnt + warp * RADIX;
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
-    const int idx = warp * (IPT * 32) + r * 32 + lane;
-    // padding of the last tile ranks behind everything (digit 255, last in index order)
-    const uint32_t d = idx < n_valid ? pass_digit<KB>(raw[r], a) : (RADIX - 1);
-    const unsigned peers = digit_peers<USE_MATCH>(d);
-    uint32_t *c = &warp_cnt[warp * RADIX + d];
-    const uint32_t cnt = *c;
+    const unsigned peers = digit_peers<USE_MATCH>(dig[r]);
+    const uint32_t cnt = wc[dig[r]];
     __syncwarp();
     const uint32_t lower = __popc(peers & lanemask_lt());
     rank[r] = cnt + lower;
-    if (lower == 0) *c = cnt + __popc(peers);
+    if (lower == 0) wc[dig[r]] = cnt + __popc(peers);
     __syncwarp();
   }
   __syncthreads();
@@ -379,7 +406,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const __grid_constant
     for (int w = 0; w < warp; w++) off += s_wsum[w];
     s_prefix[tid] += off;
     // counts published to other tiles exclude the padding of the last tile
-    valid_count = my_count - ((tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
+    valid_count = my_count - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
     uint64_t *slot = &a.lookback[(size_t)tile * RADIX + tid];
     if (tile == 0)
       st_relaxed_u64(slot, LB_FLAG_PREFIX | tagbits | (a.bin_base[tid] + valid_count));
@@ -411,30 +438,38 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const __grid_constant
   // final rank inside the tile = digit offset + offset of this warp inside the digit + rank inside warp
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
-    const int idx = warp * (IPT * 32) + r * 32 + lane;
-    const uint32_t d = idx < n_valid ? pass_digit<KB>(raw[r], a) : (RADIX - 1);
-    rank[r] += s_prefix[d] + warp_cnt[warp * RADIX + d];
-    sdigit[rank[r]] = (uint8_t)d;
-    srank[idx] = (uint16_t)rank[r];  // payload streams pick their slot up from here
+    rank[r] += s_prefix[dig[r]] + wc[dig[r]];
+    sdigit[rank[r]] = (uint8_t)dig[r];
+    srank[idx0 + r * 32] = (uint16_t)rank[r];  // payload streams pick their slot up from here
   }
 
-  // ---- move every stream ---------------------------------------------------------------------------
-  int first_stream = 0;
-  if (key_stride == KB) {
-    // SoA: the keys are already in registers
+  // ---- keys (SoA: they are already in registers), destination offsets ------------------------------------
+  const bool soa_keys = key_stride == KB;
+  if (soa_keys) {
     KeyT *kst = reinterpret_cast<KeyT *>(stage);
 #pragma unroll
-    for (int r = 0; r < IPT; r++) {
-      const int idx = warp * (IPT * 32) + r * 32 + lane;
-      if (idx < n_valid) kst[rank[r]] = raw[r];
-    }
-    __syncthreads();
-    KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
-    for (int i = tid; i < n_valid; i += THREADS) kdst[gbase[sdigit[i]] + i] = kst[i];
-    first_stream = 1;
-  } else {
-    __syncthreads();  // sdigit / gbase visible
+    for (int r = 0; r < IPT; r++)
+      if (FULL || idx0 + r * 32 < n_valid) kst[rank[r]] = raw[r];
   }
+  __syncthreads();  // staged keys, sdigit and gbase visible
+  int64_t goff[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; k++) {
+    const int i = tid + k * THREADS;
+    goff[k] = (FULL || i < n_valid) ? gbase[sdigit[i]] + i : 0;
+  }
+  int first_stream = 0;
+  if (soa_keys) {
+    const KeyT *kst = reinterpret_cast<const KeyT *>(stage);
+    KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const int i = tid + k * THREADS;
+      if (FULL || i < n_valid) kdst[goff[k]] = kst[i];
+    }
+    first_stream = 1;
+  }
+  // ---- every other stream (and, for AoS, every column of the record) ------------------------------------
   for (int s = first_stream; s < a.ss.n_streams; s++) {
     const Stream &st = a.ss.streams[s];
     const unsigned char *src = st.buf[sel];
@@ -442,15 +477,40 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const __grid_constant
     for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
       __syncthreads();  // previous use of the staging buffer is over
       const uint32_t cb = st.chunk_bytes;
-      if (cb == 8) move_chunks<uint64_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-      else if (cb == 4) move_chunks<uint32_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-      else if (cb == 16) move_chunks<uint4, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      if (cb == 8) move_chunks<uint64_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      else if (cb == 4) move_chunks<uint32_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+      else if (cb == 16) move_chunks<uint4, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
       else if constexpr (ANYCHUNK) {
-        if (cb == 2) move_chunks<uint16_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-        else move_chunks<uint8_t, THREADS, IPT>(src, dst, stage, sdigit, gbase, srank, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+        if (cb == 2) move_chunks<uint16_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
+        else move_chunks<uint8_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
       }
     }
   }
+}
+
+// ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
+// ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
+// far more registers per thread, so the narrow widths get their own instantiation.
+template <int KB, int THREADS, int IPT, int MINB, bool USE_MATCH, bool ANYCHUNK>
+__global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
+  static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
+  constexpr int TILE = THREADS * IPT;
+  constexpr int NWARPS = THREADS / 32;
+  if (a.plan->skip[a.pass]) return;
+  const uint32_t sel = a.plan->src_sel[a.pass];
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * a.stage_bytes);
+  __shared__ uint32_t s_tile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
+  for (int i = threadIdx.x; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t remaining = a.n - tile * TILE;
+  if (remaining >= TILE)
+    sweep_tile<KB, THREADS, IPT, USE_MATCH, ANYCHUNK, true>(a, smem, tile, TILE, sel);
+  else
+    sweep_tile<KB, THREADS, IPT, USE_MATCH, ANYCHUNK, false>(a, smem, tile, (int)remaining, sel);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -191,7 +191,7 @@ def test_large_properties(case):
         assert k.tobytes() == np.sort(keys).tobytes() and keys[p].tobytes() == k.tobytes()
     elif case == "f32_3streams_desc":  # BASELINE.json config 3 shape
         keys = rng.uniform(-1, 1, size=n).astype(np.float32)
-        keys[::100_003] = [0.0, -0.0, np.inf, -np.inf][: len(keys[::100_003])] if len(keys[::100_003]) >= 4 else keys[::100_003]
+        keys[:8 * 100_003:100_003] = [0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, -3.4e38]  # SURVEY 8d edge set
         i32 = np.arange(n, dtype=np.int32)
         f64 = np.arange(n, dtype=np.float64)
         u16 = (np.arange(n) % 65536).astype(np.uint16)
