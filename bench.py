@@ -349,7 +349,10 @@ def main():
 
     # ---- roofline of the dominant kernel (the digit scatter pass) ----
     peak, peak_src = measured_peak_gbs()
-    sweep_ms = [ms for step in prof for kind, ms in step if kind == "sweep"]
+    # scatter launches of skipped digit positions return at once; only executed passes count
+    sweep_all = [ms for step in prof for kind, ms in step if kind == "sweep"]
+    n_exec = max(int(stats["passes_planned"]), 1)
+    sweep_ms = sorted(sweep_all, reverse=True)[: n_exec * args.steps] if stats["algo"] == 2 else sweep_all
     per_kind = {}
     for step in prof:
         for kind, ms in step:

@@ -112,10 +112,13 @@ typedef struct b200sort_stats {
   uint32_t record_bytes;      /* sum of all stream element sizes */
   uint32_t key_bytes;
   uint32_t algo;              /* 1 LSD, 2 hybrid */
-  uint32_t passes_planned;    /* scatter passes launched */
+  uint32_t passes_planned;    /* scatter passes executed (hybrid) / launched (LSD; constant digits return at once) */
   uint32_t hist_sweeps;       /* key-only sweeps launched */
   uint32_t kernel_launches;   /* kernels launched by this call */
-  uint64_t algorithmic_bytes; /* H*N*K + P*2*N*R with the planned pass counts */
+  uint32_t segfix_passes;     /* hybrid: 1 when the in-shared-memory segment finish ran */
+  uint32_t cut_digit;         /* hybrid: digit positions below this were left to the segment finish */
+  uint32_t fell_back;         /* hybrid: 1 when a long bucket with distinct keys forced the digit-by-digit path */
+  uint64_t algorithmic_bytes; /* H*N*K + P*2*N*R with the executed pass counts */
 } b200sort_stats;
 int b200sort_last_stats(b200sort_stats *out);
 

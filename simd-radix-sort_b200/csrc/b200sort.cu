@@ -33,9 +33,10 @@ static std::atomic<uint64_t> g_launches{0};
 
 static std::atomic<int64_t> opt_algo{0};       // 0 auto, 1 LSD, 2 hybrid
 static std::atomic<int64_t> opt_tile_cfg{-1};  // -1 auto
-static std::atomic<int64_t> opt_use_match{1};
+static std::atomic<int64_t> opt_use_match{0};
 static std::atomic<int64_t> opt_allow_skip{1};
-static std::atomic<int64_t> opt_hist_match{1};
+static std::atomic<int64_t> opt_hist_match{0};
+static std::atomic<int64_t> opt_margin_bits{3};
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
 enum ProfKind { PK_HIST = 0, PK_SCAN = 1, PK_SWEEP = 2, PK_COPYBACK = 3, PK_SEGFIX = 4, PK_OTHER = 5 };
@@ -303,6 +304,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
 
   Layout L;
   make_layout(streams, n, std::min(tile, HYB_MIN_TILE), &L);
+  void *const caller_workspace = workspace;
   if (workspace == nullptr) {
     if (int rc = cached_workspace(dev, L.total, &workspace)) return rc;
   } else if (workspace_bytes < L.total) {
@@ -334,26 +336,22 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   stt.key_bytes = (uint32_t)kb;
   stt.algo = (uint32_t)algo;
 
-  if (algo == 2) {
-    HybridJob hj{};
-    hj.ss = ss; hj.n = n; hj.ko = ko; hj.ws = ws; hj.ghist = ghist; hj.tile_counter = tile_counter; hj.plan = plan;
-    hj.bin_base = bin_base; hj.lookback = lookback; hj.ctrl = (HybridCtrl *)(ws + L.hyb_off);
-    hj.sm_count = di.sm_count; hj.smem_optin = di.smem_optin; hj.stage_bytes = stage_bytes; hj.stream = stream;
-    hj.cfg = cfg; hj.use_match = opt_use_match.load() != 0;
-    int rc = hybrid_sort_u64(hj, &stt);
-    if (rc != 0) return rc;
-  } else {
-    // ---- LSD: one histogram sweep over all digit positions, then one scatter pass per digit ----
+  const bool hybrid = algo == 2;
+  {
+    // ---- one histogram sweep over all digit positions, the bucket-offset scan (+ pass plan), one
+    //      scatter pass per digit position (skipped ones return at once), segment finish, copy-back ----
     HistArgs ha{};
     ha.keys = ss.streams[0].buf[0];
     ha.stride = streams[0].elem_bytes;
-    ha.n = n; ha.ko = ko; ha.first_digit = 0; ha.n_digits = kb; ha.ghist = ghist;
+    ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist;
     CUDA_TRY(launch_hist(kb, ha, di.sm_count, stream));
 
     ScanArgs sa{};
     sa.ghist = ghist; sa.bin_base = bin_base; sa.plan = plan; sa.n = n; sa.n_passes = kb;
     for (int p = 0; p < kb; p++) sa.digit_of_pass[p] = p;
     sa.allow_skip = (int)opt_allow_skip.load();
+    sa.hybrid = hybrid ? 1 : 0;
+    sa.margin_bits = (float)opt_margin_bits.load();
     {
       ProfScope ps(PK_SCAN, stream);
       scan_kernel<<<1, RADIX, 0, stream>>>(sa);
@@ -370,6 +368,21 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
       CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, smem, opt_use_match.load() != 0, stream));
     }
+    HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
+    if (hybrid) {
+      SegfixArgs fa{};
+      fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl;
+      bool any = false;
+      for (int s = 0; s < ss.n_streams; s++) any = any || ss.streams[s].chunk_bytes < 4;
+      const unsigned grid = (unsigned)((n + SF_FT - 1) / SF_FT);
+      {
+        ProfScope ps(PK_SEGFIX, stream);
+        if (any) segfix_kernel<8, true><<<grid, SF_THREADS, 0, stream>>>(fa);
+        else segfix_kernel<8, false><<<grid, SF_THREADS, 0, stream>>>(fa);
+      }
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
     CopyBackArgs ca{};
     ca.ss = ss; ca.n = n; ca.plan = plan;
     {
@@ -381,6 +394,32 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     stt.passes_planned = (uint32_t)kb;
     stt.hist_sweeps = 1;
     stt.algorithmic_bytes = (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
+    if (hybrid) {
+      // The plan was made on the device; read it (and the fall-back flag) back.  This is the one host
+      // synchronisation of the hybrid path.
+      Plan hplan{};
+      HybridCtrl hctrl{};
+      CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaMemcpyAsync(&hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      stt.passes_planned = hplan.n_exec;
+      stt.segfix_passes = hplan.cut_digit != 0 ? 1 : 0;
+      stt.cut_digit = hplan.cut_digit;
+      stt.algorithmic_bytes = (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
+      if (hctrl.flags[0] != 0) {
+        // a long bucket with distinct keys: finish with the plain digit-by-digit path (the array is a
+        // permutation of the input, already ordered by its top digits)
+        const int64_t saved = opt_algo.exchange(1);
+        const int rc = sort_device(key_type, ascending, n, streams, stream, caller_workspace, workspace_bytes);
+        opt_algo.store(saved);
+        if (rc != 0) return rc;
+        b200sort_stats s2 = g_last_stats;
+        stt.fell_back = 1;
+        stt.passes_planned += s2.passes_planned;
+        stt.hist_sweeps += s2.hist_sweeps;
+        stt.algorithmic_bytes += s2.algorithmic_bytes;
+      }
+    }
   }
   stt.kernel_launches = (uint32_t)(g_launches.load() - launches_before);
   g_last_stats = stt;
@@ -554,6 +593,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
   if (!strcmp(name, "profile")) return &opt_profile;
+  if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
   return nullptr;
 }
 int b200sort_set_option(const char *name, int64_t value) {

@@ -74,6 +74,10 @@ struct Plan {
   uint32_t src_sel[MAX_PASSES];
   uint32_t final_sel;   // side that holds the result after the last executed pass
   uint32_t n_exec;
+  // hybrid MSB path: digit positions below cut_digit are not swept; the segment-finish kernel orders
+  // each run of keys that agree on all bits >= 8*cut_digit (0 = every varying digit is swept)
+  uint32_t cut_digit;
+  uint32_t n_const;     // digit positions on which all keys agree
 };
 
 // look-back status word: [63:62] flag, [61:57] generation tag, [56:0] value
@@ -125,10 +129,28 @@ struct HistArgs {
   uint32_t stride;      // bytes between consecutive keys (element size of stream 0)
   int64_t n;
   KeyOrder ko;
-  int first_digit;      // digit positions [first_digit, first_digit + n_digits) are counted
-  int n_digits;
+  uint32_t digit_mask;  // bit p set: digit position p is counted
   uint64_t *ghist;      // [KB][RADIX] counters, zeroed by the host
 };
+
+// One digit of one key into the block's shared-memory counters.  Lanes of a warp that all hold the same
+// digit (a constant or near-constant digit position: the common skew) are aggregated into one atomic
+// by a vote; USE_MATCH additionally aggregates arbitrary groups with __match_any_sync.
+template <bool USE_MATCH>
+__device__ __forceinline__ void hist_add(uint32_t *bins, uint32_t d, unsigned vmask) {
+  if constexpr (USE_MATCH) {
+    const unsigned peers = __match_any_sync(vmask, d);
+    if ((peers & lanemask_lt()) == 0) atomicAdd(&bins[d], (uint32_t)__popc(peers));
+  } else {
+    const int leader = __ffs(vmask) - 1;
+    const uint32_t d0 = __shfl_sync(vmask, d, leader);
+    if (__all_sync(vmask, d == d0)) {
+      if ((int)(threadIdx.x & 31) == leader) atomicAdd(&bins[d], (uint32_t)__popc(vmask));
+    } else {
+      atomicAdd(&bins[d], 1u);
+    }
+  }
+}
 
 template <int KB, int THREADS, int IPT, bool USE_MATCH>
 __global__ void __launch_bounds__(THREADS) hist_kernel(HistArgs a) {
@@ -153,14 +175,10 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(HistArgs a) {
     for (int r = 0; r < IPT; r++) {
       const unsigned vmask = __ballot_sync(0xffffffffu, valid[r]);
       if (valid[r]) {
-        for (int p = a.first_digit; p < a.first_digit + a.n_digits; p++) {
-          const uint32_t d = (uint32_t)(u[r] >> (p * RADIX_BITS)) & (RADIX - 1);
-          if constexpr (USE_MATCH) {
-            const unsigned peers = __match_any_sync(vmask, d);
-            if ((peers & lanemask_lt()) == 0) atomicAdd(&sh[p * RADIX + d], (uint32_t)__popc(peers));
-          } else {
-            atomicAdd(&sh[p * RADIX + d], 1u);
-          }
+#pragma unroll
+        for (int p = 0; p < KB; p++) {
+          if ((a.digit_mask >> p) & 1)
+            hist_add<USE_MATCH>(&sh[p * RADIX], (uint32_t)(u[r] >> (p * RADIX_BITS)) & (RADIX - 1), vmask);
         }
       }
     }
@@ -185,32 +203,64 @@ struct ScanArgs {
   int n_passes;            // passes 0..n_passes-1 in execution order
   int digit_of_pass[MAX_PASSES];
   int allow_skip;
+  int hybrid;              // 1: choose cut_digit (MSB hybrid); passes must be digit positions 0..n_passes-1
+  float margin_bits;       // hybrid: sweep top digits until their entropies sum to log2(n) + margin_bits
 };
 
 __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
   __shared__ uint64_t warp_sum[RADIX / 32];
+  __shared__ float warp_ent[RADIX / 32];
   __shared__ uint32_t s_skip[MAX_PASSES];
+  __shared__ float s_entropy[MAX_PASSES];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   if (t < MAX_PASSES) s_skip[t] = 0;
   __syncthreads();
+  const float log2n = log2f((float)a.n);
   for (int p = 0; p < a.n_passes; p++) {
     const int dp = a.digit_of_pass[p];
     const uint64_t c = a.ghist[dp * RADIX + t];
     if (a.allow_skip && c == (uint64_t)a.n) s_skip[p] = 1;
     uint64_t inc = c;
+    float e = c ? (float)c * log2f((float)c) : 0.f;  // for the digit's entropy: log2 n - sum(c log2 c)/n
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += v;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == 31) warp_sum[w] = inc;
+    if (lane == 0) warp_ent[w] = e;
     __syncthreads();
     uint64_t off = 0;
     for (int i = 0; i < w; i++) off += warp_sum[i];
     a.bin_base[p * RADIX + t] = off + inc - c;
+    if (t == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < RADIX / 32; i++) tot += warp_ent[i];
+      s_entropy[p] = fmaxf(log2n - tot / (float)a.n, 0.f);
+    }
     __syncthreads();
   }
   if (t == 0) {
+    uint32_t cut = 0, n_const = 0;
+    for (int p = 0; p < a.n_passes; p++) n_const += s_skip[p];
+    if (a.hybrid) {
+      // MSB hybrid: sweep only the top digits whose (marginal) entropies add up to log2(n) + margin; the
+      // runs that still agree on those digits are then short (expected length 2^-margin) or constant, and
+      // segfix_kernel finishes them in shared memory.  A cut that saves fewer than two sweeps is not
+      // worth the finishing pass.
+      float acc = 0.f;
+      const float need = log2n + a.margin_bits;
+      for (int p = a.n_passes - 1; p >= 0; p--) {
+        if (!s_skip[p]) acc += s_entropy[p];
+        if (acc >= need) { cut = (uint32_t)p; break; }
+      }
+      uint32_t saved = 0;
+      for (uint32_t p = 0; p < cut; p++) saved += s_skip[p] ? 0 : 1;
+      if (saved < 2) cut = 0;
+      for (uint32_t p = 0; p < cut; p++) s_skip[p] = 1;
+    }
     uint32_t sel = 0, n_exec = 0;
     for (int p = 0; p < a.n_passes; p++) {
       a.plan->skip[p] = s_skip[p];
@@ -219,6 +269,8 @@ __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
     }
     a.plan->final_sel = sel;
     a.plan->n_exec = n_exec;
+    a.plan->cut_digit = cut;
+    a.plan->n_const = n_const;
   }
 }
 
@@ -523,7 +575,7 @@ struct CopyBackArgs {
 };
 
 __global__ void __launch_bounds__(256) copyback_kernel(const __grid_constant__ CopyBackArgs a) {
-  if (a.plan->final_sel == 0) return;
+  if (a.plan->final_sel == 0 || a.plan->cut_digit != 0) return;  // (the segment finish already wrote side 0)
   for (int s = 0; s < a.ss.n_streams; s++) {
     const Stream &st = a.ss.streams[s];
     const size_t bytes = (size_t)a.n * st.chunk_bytes * st.chunks_per_elem;

@@ -250,3 +250,77 @@ def test_caller_workspace_and_stats():
     with pytest.raises(S.B200SortError) as ei:
         S.sort(n, k, p, workspace=small)
     assert ei.value.code == -4
+
+
+# ------------------------------------------------------------------------------------------------
+# MSB hybrid path (8-byte keys): top-digit sweeps + in-shared-memory segment finish
+# ------------------------------------------------------------------------------------------------
+def _hybrid_cases(n, rng):
+    u = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    yield "uniform_u64", u, np.uint64
+    yield "uniform_i64", u.view(np.int64).copy(), np.int64
+    yield "f64_uniform", rng.uniform(-1, 1, size=n), np.float64
+    yield "f64_gauss", rng.normal(0, 1, size=n), np.float64
+    yield "i64_gauss100", np.round(rng.normal(0, 100, size=n)).astype(np.int64), np.int64
+    yield "few_unique", rng.integers(-8, 8, size=n, dtype=np.int64), np.int64
+    yield "zero", np.zeros(n, np.int64), np.int64
+    yield "zero_one", rng.integers(0, 2, size=n).astype(np.uint64), np.uint64
+    table = rng.integers(-2**63, 2**63 - 1, size=1 << 12, dtype=np.int64)
+    yield "dups_of_4096_values", table[rng.integers(0, 1 << 12, size=n)], np.int64
+    yield "sorted", np.sort(u), np.uint64
+    yield "small_range_u64", rng.integers(0, 1 << 20, size=n, dtype=np.uint64), np.uint64
+    # top digits look high-entropy but are a function of a group id: medium (100) and long (1000) buckets
+    # with distinct keys -> rank loop, resp. the fall-back to the digit-by-digit path
+    for glen, tag in ((100, "medium_segments"), (1000, "long_segments_fallback")):
+        g = np.arange(n) // glen
+        f = rng.integers(0, 2**32, size=g.max() + 1, dtype=np.uint64)
+        yield tag, (f[g] << np.uint64(32)) | rng.integers(0, 2**32, size=n, dtype=np.uint64), np.uint64
+
+
+@pytest.mark.parametrize("n", [1, 17, 2049, 300_000, (1 << 20) + 77])
+def test_hybrid_msb_path_matches_total_order(n):
+    rng = np.random.default_rng(n)
+    try:
+        S.set_option("algo", 2)
+        for name, keys, dt in _hybrid_cases(n, rng):
+            keys = np.ascontiguousarray(keys.astype(dt))
+            for up in (True, False):
+                idx = np.arange(n, dtype=np.uint32)
+                k, (p,) = gpu_sort_soa(keys, [idx], up)
+                want = O.total_order_sorted_keys(keys, up)
+                assert k.tobytes() == want.tobytes(), (name, n, up)
+                assert np.array_equal(np.sort(p), idx) and keys[p].tobytes() == k.tobytes(), (name, n, up)
+            if name == "long_segments_fallback" and n >= 300_000:
+                assert S.last_stats()["fell_back"] == 1
+            if name == "uniform_u64" and n >= 300_000:
+                st = S.last_stats()
+                assert st["algo"] == 2 and st["fell_back"] == 0 and st["cut_digit"] >= 2 and st["segfix_passes"] == 1
+    finally:
+        S.set_option("algo", 0)
+
+
+def test_hybrid_aos_and_multi_stream():
+    n = 500_000
+    rng = np.random.default_rng(5)
+    try:
+        S.set_option("algo", 2)
+        keys = rng.integers(-2**63, 2**63 - 1, size=n, dtype=np.int64)
+        keys[::7] = keys[3]  # duplicates
+        rec = np.zeros((n, 32), np.uint8)
+        rec[:, :8] = keys.view(np.uint8).reshape(n, 8)
+        rec[:, 8:16] = np.arange(n, dtype=np.int64).view(np.uint8).reshape(n, 8)
+        r = dev(rec)
+        S.sort_combined(n, r, np.int64, up=False)
+        out = host(r)
+        ok = np.ascontiguousarray(out[:, :8]).reshape(-1).view(np.int64)
+        op = np.ascontiguousarray(out[:, 8:16]).reshape(-1).view(np.int64)
+        assert ok.tobytes() == np.sort(keys)[::-1].tobytes()
+        assert np.array_equal(keys[op], ok) and np.array_equal(np.sort(op), np.arange(n))
+        # SoA with three payload streams incl. a 2-byte one (ANYCHUNK instantiations)
+        fk = rng.uniform(-1, 1, size=n)
+        a, b, c = np.arange(n, dtype=np.int32), np.arange(n, dtype=np.float64), (np.arange(n) % 65536).astype(np.uint16)
+        k, (pa, pb_, pc) = gpu_sort_soa(fk, [a, b, c], True)
+        assert k.tobytes() == np.sort(fk).tobytes() and fk[pa].tobytes() == k.tobytes()
+        assert np.array_equal(pb_, pa.astype(np.float64)) and np.array_equal(pc, (pa % 65536).astype(np.uint16))
+    finally:
+        S.set_option("algo", 0)
