@@ -36,7 +36,7 @@ static std::atomic<int64_t> opt_tile_cfg{-1};  // -1 auto
 static std::atomic<int64_t> opt_use_match{0};
 static std::atomic<int64_t> opt_allow_skip{1};
 static std::atomic<int64_t> opt_hist_match{0};
-static std::atomic<int64_t> opt_margin_bits{3};
+static std::atomic<int64_t> opt_margin_bits{2};
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
 enum ProfKind { PK_HIST = 0, PK_SCAN = 1, PK_SWEEP = 2, PK_COPYBACK = 3, PK_SEGFIX = 4, PK_OTHER = 5 };
@@ -108,7 +108,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
 struct TileCfg { int threads, ipt; };
-static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 8}};
+static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 8}, {256, 16}, {256, 8}};
 static constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 
 static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes) {
@@ -116,14 +116,17 @@ static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes) {
   return tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3;
 }
 
+static std::atomic<int64_t> opt_scatter_mode{0};  // 0 staged (coalesced), 1 payloads direct, 2 keys + payloads direct
+
 template <int KB, int THREADS, int IPT, int MINB>
-static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match, cudaStream_t st) {
+static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem, int mode, cudaStream_t st) {
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   for (int s = (a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == KB) ? 1 : 0; s < a.ss.n_streams; s++)
     any = any || a.ss.streams[s].chunk_bytes < 4;
   void (*k)(const SweepArgs);
-  if (any) k = use_match ? onesweep_kernel<KB, THREADS, IPT, MINB, true, true> : onesweep_kernel<KB, THREADS, IPT, MINB, false, true>;
-  else k = use_match ? onesweep_kernel<KB, THREADS, IPT, MINB, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, false, false>;
+  if (mode == 2) k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false>;
+  else if (mode == 1) k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false>;
+  else k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 0, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 0, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
@@ -133,23 +136,23 @@ static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t sm
 }
 
 template <int KB>
-static cudaError_t launch_sweep_kb(int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match,
-                                   cudaStream_t st) {
+static cudaError_t launch_sweep_kb(int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, int mode, cudaStream_t st) {
   switch (cfg) {
-    case 0: return launch_sweep_t<KB, 512, 16, 1>(a, n_tiles, smem, use_match, st);
-    case 1: return launch_sweep_t<KB, 256, 16, 3>(a, n_tiles, smem, use_match, st);
-    case 2: return launch_sweep_t<KB, 512, 8, 2>(a, n_tiles, smem, use_match, st);
-    default: return launch_sweep_t<KB, 256, 8, 4>(a, n_tiles, smem, use_match, st);
+    case 0: return launch_sweep_t<KB, 512, 16, 1>(a, n_tiles, smem, mode, st);
+    case 1: return launch_sweep_t<KB, 256, 16, 3>(a, n_tiles, smem, mode, st);
+    case 2: return launch_sweep_t<KB, 512, 8, 2>(a, n_tiles, smem, mode, st);
+    case 3: return launch_sweep_t<KB, 256, 8, 4>(a, n_tiles, smem, mode, st);
+    case 4: return launch_sweep_t<KB, 256, 16, 2>(a, n_tiles, smem, mode, st);
+    default: return launch_sweep_t<KB, 256, 8, 3>(a, n_tiles, smem, mode, st);
   }
 }
 
-static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, bool use_match,
-                                cudaStream_t st) {
+static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, int mode, cudaStream_t st) {
   switch (kb) {
-    case 1: return launch_sweep_kb<1>(cfg, a, n_tiles, smem, use_match, st);
-    case 2: return launch_sweep_kb<2>(cfg, a, n_tiles, smem, use_match, st);
-    case 4: return launch_sweep_kb<4>(cfg, a, n_tiles, smem, use_match, st);
-    default: return launch_sweep_kb<8>(cfg, a, n_tiles, smem, use_match, st);
+    case 1: return launch_sweep_kb<1>(cfg, a, n_tiles, smem, mode, st);
+    case 2: return launch_sweep_kb<2>(cfg, a, n_tiles, smem, mode, st);
+    case 4: return launch_sweep_kb<4>(cfg, a, n_tiles, smem, mode, st);
+    default: return launch_sweep_kb<8>(cfg, a, n_tiles, smem, mode, st);
   }
 }
 
@@ -240,7 +243,7 @@ struct Layout {
 
 static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin) {
   int cfg = (int)opt_tile_cfg.load();
-  if (cfg < 0 || cfg >= kNumTileCfgs) cfg = (kb >= 4) ? 0 : 0;
+  if (cfg < 0 || cfg >= kNumTileCfgs) cfg = 1;
   // fall back to a smaller tile if the staging buffer would not fit
   while (sweep_smem_bytes(kTileCfgs[cfg], stage_bytes) > smem_optin && cfg != 1) cfg = 1;
   return cfg;
@@ -366,7 +369,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       wa.bin_base = bin_base + (size_t)p * RADIX;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
-      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, smem, opt_use_match.load() != 0, stream));
+      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, smem, (int)opt_scatter_mode.load(), stream));
     }
     HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
     if (hybrid) {
@@ -594,6 +597,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
+  if (!strcmp(name, "scatter_mode")) return &opt_scatter_mode;
   return nullptr;
 }
 int b200sort_set_option(const char *name, int64_t value) {

@@ -61,9 +61,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
   const uint32_t sel = a.plan->final_sel;
 
   __shared__ O wkey[SF_W];
-  __shared__ int16_t sstart[SF_W];
-  __shared__ int16_t send[SF_W];
-  __shared__ int s_tot[SF_THREADS];
+  __shared__ uint32_t hbits[SF_W / 32 + 2];  // one bit per window position: set = first key of a segment
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t s0 = (int64_t)blockIdx.x * SF_FT;
@@ -76,7 +74,12 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
   const Stream &ks = a.ss.streams[0];
   const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
   const unsigned char *ksrc = ks.buf[sel];
-  for (int p = tid; p < wn; p += SF_THREADS) wkey[p] = to_ordered<KB>(load_key<KB>(ksrc, w0 + p, key_stride), a.ko);
+#pragma unroll
+  for (int k = 0; k < SF_PPT; k++) {
+    const int p = tid + k * SF_THREADS;
+    if (p < wn) wkey[p] = to_ordered<KB>(load_key<KB>(ksrc, w0 + p, key_stride), a.ko);
+  }
+  if (tid < 2) hbits[SF_W / 32 + tid] = 0;
   __syncthreads();
 
   // a position is a segment head when its prefix differs from its left neighbour's
@@ -84,83 +87,32 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
     if (p == 0) return w0 == 0;  // unknown when the window does not start at the array start
     return ((wkey[p] ^ wkey[p - 1]) & pmask) != 0;
   };
-
-  // ---- segment start of every window position: running max of head positions (blocked scan) ------
-  const int pb = tid * SF_PPT;
-  int loc[SF_PPT];
-  int run = -1;
+  // head bits, one 32-bit word per warp and step; the array end closes the last segment
 #pragma unroll
-  for (int j = 0; j < SF_PPT; j++) {
-    const int p = pb + j;
-    if (p < wn && is_head(p)) run = p;
-    loc[j] = run;
+  for (int k = 0; k < SF_PPT; k++) {
+    const int p = tid + k * SF_THREADS;
+    const bool h = (p < wn && is_head(p)) || (p == wn && w1 == a.n);
+    const unsigned word = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) hbits[warp + k * (SF_THREADS / 32)] = word;
   }
-  s_tot[tid] = run;
-  __syncthreads();
-  {
-    // exclusive prefix max over the threads before this one
-    // = max over the warps before this one (warp-wide reductions) and over the lower lanes of this warp
-    int ex = -1;
-    for (int t = 0; t < (warp << 5); t += 32) {
-      int m = s_tot[t + lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-      ex = max(ex, m);
-    }
-    int own = s_tot[tid];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, own, o);
-      if (lane >= o) own = max(own, u);
-    }
-    const int prev = __shfl_up_sync(0xffffffffu, own, 1);
-    if (lane > 0) ex = max(ex, prev);
-#pragma unroll
-    for (int j = 0; j < SF_PPT; j++) {
-      const int p = pb + j;
-      if (p < wn) sstart[p] = (int16_t)(loc[j] >= 0 ? loc[j] : ex);
-    }
-  }
+  if (tid == 0 && wn == SF_W && w1 == a.n) hbits[SF_W / 32] = 1u;
   __syncthreads();
 
-  // ---- segment end (position of the next head to the right): running min from the right ------------
-  run = SF_BIG;
-#pragma unroll
-  for (int j = SF_PPT - 1; j >= 0; j--) {
-    const int p = pb + j;
-    loc[j] = run;
-    if (p < wn && is_head(p)) run = p;
-  }
-  s_tot[tid] = run;
-  __syncthreads();
-  {
-    int ex = SF_BIG;
-    for (int t = ((warp + 1) << 5); t < SF_THREADS; t += 32) {
-      int m = s_tot[t + lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-      ex = min(ex, m);
-    }
-    int own = s_tot[tid];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_down_sync(0xffffffffu, own, o);
-      if (lane + o < 32) own = min(own, u);
-    }
-    const int next = __shfl_down_sync(0xffffffffu, own, 1);
-    if (lane < 31) ex = min(ex, next);
-    const int end_of_window = (w1 == a.n) ? wn : SF_BIG;  // the array end closes the last segment
-#pragma unroll
-    for (int j = 0; j < SF_PPT; j++) {
-      const int p = pb + j;
-      if (p < wn) {
-        int e = loc[j] != SF_BIG ? loc[j] : ex;
-        if (e == SF_BIG) e = end_of_window;
-        send[p] = (int16_t)e;
-      }
-    }
-  }
-  __syncthreads();
+  constexpr int MAXWORDS = SF_MAXSEG / 32;
+  // start of the segment holding p: the nearest head at or before p (-1: none within SF_MAXSEG)
+  auto seg_start = [&](int p) -> int {
+    int w = p >> 5;
+    uint32_t m = hbits[w] & (0xffffffffu >> (31 - (p & 31)));
+    for (int s = 0; m == 0 && w > 0 && s < MAXWORDS; s++) m = hbits[--w];
+    return m ? (w << 5) + 31 - __clz(m) : -1;
+  };
+  // end of the segment holding p: the nearest head after p (SF_BIG: none within SF_MAXSEG)
+  auto seg_end = [&](int p) -> int {
+    int w = p >> 5;
+    uint32_t m = (p & 31) == 31 ? 0u : (hbits[w] & (0xffffffffu << ((p & 31) + 1)));
+    for (int s = 0; m == 0 && w < SF_W / 32 && s < MAXWORDS; s++) m = hbits[++w];
+    return m ? (w << 5) + __ffs(m) - 1 : SF_BIG;
+  };
 
   // ---- classify every position this thread moves; rank inside short segments ---------------------------
   int dest[SF_PPT];
@@ -171,7 +123,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
     const int p = tid + k * SF_THREADS;
     dest[k] = p;
     if (p < wn) {
-      const int st = sstart[p], en = send[p];
+      const int st = seg_start(p), en = seg_end(p);
       const int64_t gp = w0 + p;
       const bool is_long = st < 0 || en == SF_BIG || (en - st) > SF_MAXSEG;
       if (is_long) {
@@ -199,6 +151,12 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
     }
   }
   if (__any_sync(0xffffffffu, fail) && lane == 0) atomicOr(&a.ctrl->flags[0], 1u);
+  if (sel == 0) {
+    // the swept data already lies in the caller's arrays: only displaced elements have to move
+#pragma unroll
+    for (int k = 0; k < SF_PPT; k++)
+      if (dest[k] == tid + k * SF_THREADS) active &= ~(1u << k);
+  }
 
   // ---- move every stream: window position p -> dest (side `sel` -> side 0) ----------------------------------
   for (int s = 0; s < a.ss.n_streams; s++) {

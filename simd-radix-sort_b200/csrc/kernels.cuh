@@ -340,10 +340,11 @@ __device__ __forceinline__ uint32_t lut_digit(typename UIntOf<KB>::type raw, con
 
 // Moves one chunk column of one stream through the staging buffer.  goff[k] is the destination element
 // index of staged slot tid + k*THREADS (computed once per tile, shared by all streams).
-template <typename T, int THREADS, int IPT, bool FULL>
-__device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
-                                            const uint16_t *srank, const int64_t (&goff)[IPT], int64_t tile_base,
-                                            int n_valid, uint32_t cpe, uint32_t c, int warp, int lane) {
+template <typename T, int THREADS, int IPT, bool FULL, bool CPE1>
+__device__ __forceinline__ void move_chunks_t(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
+                                              const uint16_t *srank, const int64_t (&goff)[IPT], int64_t tile_base,
+                                              int n_valid, uint32_t cpe_rt, uint32_t c, int warp, int lane) {
+  const uint32_t cpe = CPE1 ? 1u : cpe_rt;  // one chunk per element (the common shapes): no index multiplies
   T *stage = reinterpret_cast<T *>(stage_raw);
   const int idx0 = warp * (IPT * 32) + lane;
   const T *s = reinterpret_cast<const T *>(src) + ((size_t)(tile_base + idx0) * cpe + c);
@@ -371,7 +372,38 @@ __device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned c
   }
 }
 
-template <int KB, int THREADS, int IPT, bool USE_MATCH, bool ANYCHUNK, bool FULL>
+template <typename T, int THREADS, int IPT, bool FULL>
+__device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
+                                            const uint16_t *srank, const int64_t (&goff)[IPT], int64_t tile_base,
+                                            int n_valid, uint32_t cpe, uint32_t c, int warp, int lane) {
+  if (cpe == 1)
+    move_chunks_t<T, THREADS, IPT, FULL, true>(src, dst, stage_raw, srank, goff, tile_base, n_valid, 1, 0, warp, lane);
+  else
+    move_chunks_t<T, THREADS, IPT, FULL, false>(src, dst, stage_raw, srank, goff, tile_base, n_valid, cpe, c, warp, lane);
+}
+
+// Direct scatter of one chunk column of one stream: item r of this thread (tile index idx0 + 32 r) goes to
+// element g[r] of the destination.
+template <typename T, int IPT, bool FULL>
+__device__ __forceinline__ void direct_chunks(const unsigned char *src, unsigned char *dst, const int64_t (&g)[IPT],
+                                              int64_t first_item, int idx0, int n_valid, uint32_t cpe, uint32_t c) {
+  const T *s = reinterpret_cast<const T *>(src) + ((size_t)first_item * cpe + c);
+  T *d = reinterpret_cast<T *>(dst) + c;
+  constexpr int BATCH_MAX = sizeof(T) == 16 ? 4 : 8;
+  constexpr int BATCH = BATCH_MAX < IPT ? BATCH_MAX : IPT;
+#pragma unroll
+  for (int r0 = 0; r0 < IPT; r0 += BATCH) {
+    T v[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; b++)
+      if (FULL || idx0 + (r0 + b) * 32 < n_valid) v[b] = s[(size_t)((r0 + b) * 32) * cpe];
+#pragma unroll
+    for (int b = 0; b < BATCH; b++)
+      if (FULL || idx0 + (r0 + b) * 32 < n_valid) d[(size_t)g[r0 + b] * cpe] = v[b];
+  }
+}
+
+template <int KB, int THREADS, int IPT, int MODE, bool ANYCHUNK, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
                                            const uint32_t sel) {
   constexpr int TILE = THREADS * IPT;
@@ -394,38 +426,32 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
   const unsigned char *kp = ks.buf[sel] + (size_t)(tile_base + idx0) * key_stride;
 
-  // ---- load keys, digits ---------------------------------------------------------------------------
+  // ---- load keys ------------------------------------------------------------------------------------
   KeyT raw[IPT];
-  uint32_t dig[IPT];
 #pragma unroll
   for (int r = 0; r < IPT; r++)
     raw[r] = (FULL || idx0 + r * 32 < n_valid) ? *reinterpret_cast<const KeyT *>(kp + (size_t)(r * 32) * key_stride) : (KeyT)0;
-  if (a.lut == nullptr) {
-    const DigitX dx = make_digitx(a.ko, a.shift);
-#pragma unroll
-    for (int r = 0; r < IPT; r++) dig[r] = fast_digit<KB>(raw[r], dx);
-  } else {
-#pragma unroll
-    for (int r = 0; r < IPT; r++) dig[r] = lut_digit<KB>(raw[r], a);
-  }
-  if (!FULL) {
+  // The digit of item r is recomputed where it is needed instead of being kept in IPT registers.
+  const DigitX dx = make_digitx(a.ko, a.shift);
+  const bool use_lut = a.lut != nullptr;
+  auto digit_of = [&](int r) -> uint32_t {
     // padding of the last tile ranks behind everything (digit 255, last in index order)
-#pragma unroll
-    for (int r = 0; r < IPT; r++)
-      if (idx0 + r * 32 >= n_valid) dig[r] = RADIX - 1;
-  }
+    if (!FULL && idx0 + r * 32 >= n_valid) return RADIX - 1;
+    return use_lut ? lut_digit<KB>(raw[r], a) : fast_digit<KB>(raw[r], dx);
+  };
 
   // ---- rank inside the warp (stable) -----------------------------------------------------------------
   uint32_t rank[IPT];
   uint32_t *wc = warp_cnt + warp * RADIX;
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
-    const unsigned peers = digit_peers<USE_MATCH>(dig[r]);
-    const uint32_t cnt = wc[dig[r]];
+    const uint32_t d = digit_of(r);
+    const unsigned peers = digit_peers<false>(d);  // ballots: measured faster than MATCH.ANY on B200
+    const uint32_t cnt = wc[d];
     __syncwarp();
     const uint32_t lower = __popc(peers & lanemask_lt());
     rank[r] = cnt + lower;
-    if (lower == 0) wc[dig[r]] = cnt + __popc(peers);
+    if (lower == 0) wc[d] = cnt + __popc(peers);
     __syncwarp();
   }
   __syncthreads();
@@ -467,43 +493,102 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   }
   __syncthreads();  // s_prefix complete
 
-  // ---- decoupled look-back (one thread per digit) while the other warps stage the keys --------------
-  if (tid < RADIX) {
-    uint64_t excl;
-    if (tile == 0) {
-      excl = a.bin_base[tid];
-    } else {
-      excl = 0;
-      int64_t t = tile - 1;
-      while (true) {
-        const uint64_t w = ld_relaxed_u64(&a.lookback[(size_t)t * RADIX + tid]);
-        if ((w & LB_TAG_MASK) != tagbits || (w & LB_FLAG_MASK) == 0) continue;  // not published yet
-        excl += w & LB_VALUE_MASK;
-        if ((w & LB_FLAG_MASK) == LB_FLAG_PREFIX) break;
-        t--;
-      }
-      st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
-    }
-    gbase[tid] = (int64_t)excl - (int64_t)s_prefix[tid];
-  }
-
   // final rank inside the tile = digit offset + offset of this warp inside the digit + rank inside warp
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
-    rank[r] += s_prefix[dig[r]] + wc[dig[r]];
-    sdigit[rank[r]] = (uint8_t)dig[r];
-    srank[idx0 + r * 32] = (uint16_t)rank[r];  // payload streams pick their slot up from here
+    const uint32_t d = digit_of(r);
+    rank[r] += s_prefix[d] + wc[d];
+    if (MODE != 2) sdigit[rank[r]] = (uint8_t)d;
+    if (MODE == 0) srank[idx0 + r * 32] = (uint16_t)rank[r];  // payload streams pick their slot up from here
   }
 
-  // ---- keys (SoA: they are already in registers), destination offsets ------------------------------------
+  // ---- keys into the staging buffer (SoA: they are already in registers) ---------------------------------
   const bool soa_keys = key_stride == KB;
-  if (soa_keys) {
+  if (MODE != 2 && soa_keys) {
     KeyT *kst = reinterpret_cast<KeyT *>(stage);
 #pragma unroll
     for (int r = 0; r < IPT; r++)
       if (FULL || idx0 + r * 32 < n_valid) kst[rank[r]] = raw[r];
   }
+
+  // ---- decoupled look-back (one thread per digit), after the staging stores so that the predecessors
+  //      have had time to publish.  LB_BATCH predecessors are polled per round trip: the chain of
+  //      dependent L2 loads is what this phase costs. ------------------------------------------------------
+  if (tid < RADIX) {
+    uint64_t excl;
+    if (tile == 0) {
+      excl = a.bin_base[tid];
+    } else {
+      constexpr int LB_BATCH = 4;
+      excl = 0;
+      int64_t t = tile - 1;
+      bool done = false;
+      while (!done) {
+        uint64_t w[LB_BATCH];
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; j++) {
+          const int64_t tt = t - j;
+          w[j] = tt >= 0 ? ld_relaxed_u64(&a.lookback[(size_t)tt * RADIX + tid]) : (LB_FLAG_PREFIX | tagbits);
+        }
+        int consumed = 0;
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; j++) {
+          const bool ready = (w[j] & LB_TAG_MASK) == tagbits && (w[j] & LB_FLAG_MASK) != 0;
+          if (!done && consumed == j && ready) {  // consume in order, stop at the first unpublished word
+            excl += w[j] & LB_VALUE_MASK;
+            consumed = j + 1;
+            if ((w[j] & LB_FLAG_MASK) == LB_FLAG_PREFIX) done = true;
+          }
+        }
+        t -= consumed;
+      }
+      st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
+    }
+    gbase[tid] = (int64_t)excl - (int64_t)s_prefix[tid];
+  }
   __syncthreads();  // staged keys, sdigit and gbase visible
+
+  if constexpr (MODE != 0) {
+    // ---- direct scatter: every item goes from registers straight to its final address.  The writes of
+    //      one warp instruction fall into up to 32 different buckets; the 126 MB L2 merges the partial
+    //      sectors of neighbouring tiles before they reach HBM (ncu: dram bytes ~ algorithmic bytes). ----
+    int64_t g[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) g[r] = gbase[digit_of(r)] + rank[r];
+    int first_stream = 0;
+    if (soa_keys) {
+      KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
+      if (MODE == 2) {
+#pragma unroll
+        for (int r = 0; r < IPT; r++)
+          if (FULL || idx0 + r * 32 < n_valid) kdst[g[r]] = raw[r];
+      } else {
+        const KeyT *kst = reinterpret_cast<const KeyT *>(stage);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+          const int i = tid + k * THREADS;
+          if (FULL || i < n_valid) kdst[gbase[sdigit[i]] + i] = kst[i];
+        }
+      }
+      first_stream = 1;
+    }
+    for (int s = first_stream; s < a.ss.n_streams; s++) {
+      const Stream &st = a.ss.streams[s];
+      const unsigned char *src = st.buf[sel];
+      unsigned char *dst = st.buf[sel ^ 1];
+      const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
+      for (uint32_t c = 0; c < cpe; c++) {
+        if (cb == 8) direct_chunks<uint64_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
+        else if (cb == 4) direct_chunks<uint32_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
+        else if (cb == 16) direct_chunks<uint4, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
+        else if constexpr (ANYCHUNK) {
+          if (cb == 2) direct_chunks<uint16_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
+          else direct_chunks<uint8_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
+        }
+      }
+    }
+    return;
+  } else {
   int64_t goff[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
@@ -538,12 +623,13 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       }
     }
   }
+  }
 }
 
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
 // ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
 // far more registers per thread, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, int MINB, bool USE_MATCH, bool ANYCHUNK>
+template <int KB, int THREADS, int IPT, int MINB, int MODE, bool ANYCHUNK>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
@@ -560,9 +646,9 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
   if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, USE_MATCH, ANYCHUNK, true>(a, smem, tile, TILE, sel);
+    sweep_tile<KB, THREADS, IPT, MODE, ANYCHUNK, true>(a, smem, tile, TILE, sel);
   else
-    sweep_tile<KB, THREADS, IPT, USE_MATCH, ANYCHUNK, false>(a, smem, tile, (int)remaining, sel);
+    sweep_tile<KB, THREADS, IPT, MODE, ANYCHUNK, false>(a, smem, tile, (int)remaining, sel);
 }
 
 // ------------------------------------------------------------------------------------------------

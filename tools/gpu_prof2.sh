@@ -7,7 +7,4 @@ $CMD > gpurun_out/prof2_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:onesweep -s 12 -c 1 -o gpurun_out/prof2_sweep $CMD > gpurun_out/prof2_ncu.log 2>&1
 $CMD > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:segfix -s 1 -c 1 -o gpurun_out/prof2_segfix $CMD >> gpurun_out/prof2_ncu.log 2>&1
-$CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:hist_kernel -s 1 -c 1 -o gpurun_out/prof2_hist $CMD >> gpurun_out/prof2_ncu.log 2>&1
-cat gpurun_out/prof2_plain.log; tail -3 gpurun_out/prof2_ncu.log
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest4.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest4.log
+cat gpurun_out/prof2_plain.log; tail -3 gpurun_out/prof2_ncu.log; ls -la gpurun_out
