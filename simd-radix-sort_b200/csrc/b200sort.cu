@@ -111,22 +111,34 @@ struct TileCfg { int threads, ipt; };
 static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 8}, {256, 16}, {256, 8}};
 static constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 
-static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes) {
+static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1) {
   const size_t tile = (size_t)c.threads * c.ipt;
-  return tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3;
+  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3;
 }
 
-static std::atomic<int64_t> opt_scatter_mode{0};  // 0 staged (coalesced), 1 payloads direct, 2 keys + payloads direct
+static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
 
 template <int KB, int THREADS, int IPT, int MINB>
-static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem, int mode, cudaStream_t st) {
+static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int mode, cudaStream_t st) {
+  (void)mode;
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
-  for (int s = (a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == KB) ? 1 : 0; s < a.ss.n_streams; s++)
+  int n_cols = 0;
+  const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == KB;
+  for (int s = soa ? 1 : 0; s < a.ss.n_streams; s++) {
     any = any || a.ss.streams[s].chunk_bytes < 4;
+    n_cols += (int)a.ss.streams[s].chunks_per_elem;
+  }
+  n_cols += soa ? 1 : 0;
+  const TileCfg tc{THREADS, IPT};
+  // double-buffer the columns when there is more than one and MINB CTAs still fit on an SM
+  int nstage = (int)opt_nstage.load();
+  if (nstage != 1 && nstage != 2)
+    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * MINB <= smem_optin + 1024) ? 2 : 1;
+  if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2) > smem_optin) nstage = 1;
+  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage);
   void (*k)(const SweepArgs);
-  if (mode == 2) k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false>;
-  else if (mode == 1) k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false>;
-  else k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 0, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 0, false>;
+  if (nstage == 2) k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false>;
+  else k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
@@ -369,7 +381,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       wa.bin_base = bin_base + (size_t)p * RADIX;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
-      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, smem, (int)opt_scatter_mode.load(), stream));
+      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, 0, stream));
     }
     HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
     if (hybrid) {
@@ -597,7 +609,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
-  if (!strcmp(name, "scatter_mode")) return &opt_scatter_mode;
+  if (!strcmp(name, "nstage")) return &opt_nstage;
   return nullptr;
 }
 int b200sort_set_option(const char *name, int64_t value) {

@@ -338,33 +338,50 @@ __device__ __forceinline__ uint32_t lut_digit(typename UIntOf<KB>::type raw, con
   return a.lut[(uint32_t)(to_ordered<KB>(raw, a.ko) >> a.lut_shift)];
 }
 
-// Moves one chunk column of one stream through the staging buffer.  goff[k] is the destination element
-// index of staged slot tid + k*THREADS (computed once per tile, shared by all streams).
-template <typename T, int THREADS, int IPT, bool FULL, bool CPE1>
-__device__ __forceinline__ void move_chunks_t(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
-                                              const uint16_t *srank, const int64_t (&goff)[IPT], int64_t tile_base,
-                                              int n_valid, uint32_t cpe_rt, uint32_t c, int warp, int lane) {
-  const uint32_t cpe = CPE1 ? 1u : cpe_rt;  // one chunk per element (the common shapes): no index multiplies
-  T *stage = reinterpret_cast<T *>(stage_raw);
-  const int idx0 = warp * (IPT * 32) + lane;
-  const T *s = reinterpret_cast<const T *>(src) + ((size_t)(tile_base + idx0) * cpe + c);
-  T *d = reinterpret_cast<T *>(dst) + c;
+// ---- staging of one chunk column of one stream ---------------------------------------------------------
+// cp.async (LDGSTS) copies every item straight from global memory into its bucket-ordered slot of a
+// staging buffer: no register round trip, and the loads stay in flight while the CTA does the look-back
+// and writes the previous column out.
+template <int CB>
+__device__ __forceinline__ void cp_async(uint32_t smem_addr, const void *gptr) {
+  if constexpr (CB == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(gptr), "n"(CB) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CB, int IPT, bool FULL>
+__device__ __forceinline__ void stage_async(const unsigned char *src, unsigned char *buf, const uint16_t *srank, int64_t tile_base,
+                                            int idx0, int n_valid, uint32_t cpe, uint32_t c) {
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(buf);
+  const unsigned char *s = src + ((size_t)(tile_base + idx0) * cpe + c) * CB;
   const uint16_t *sr = srank + idx0;
-  // loads are issued in batches of up to 8 chunks (4 for 16-byte chunks) per thread to bound register use
-  constexpr int BATCH_MAX = sizeof(T) == 16 ? 4 : 8;
-  constexpr int BATCH = BATCH_MAX < IPT ? BATCH_MAX : IPT;
-  static_assert(IPT % BATCH == 0, "IPT must be a multiple of the load batch");
-#pragma unroll 1
-  for (int r0 = 0; r0 < IPT; r0 += BATCH) {
-    T v[BATCH];
 #pragma unroll
-    for (int b = 0; b < BATCH; b++)
-      if (FULL || idx0 + (r0 + b) * 32 < n_valid) v[b] = s[(size_t)((r0 + b) * 32) * cpe];
+  for (int r = 0; r < IPT; r++)
+    if (FULL || idx0 + r * 32 < n_valid) cp_async<CB>(base + (uint32_t)sr[r * 32] * CB, s + (size_t)(r * 32) * cpe * CB);
+}
+
+template <typename T, int IPT, bool FULL>
+__device__ __forceinline__ void stage_sync(const unsigned char *src, unsigned char *buf, const uint16_t *srank, int64_t tile_base,
+                                           int idx0, int n_valid, uint32_t cpe, uint32_t c) {
+  T *stage = reinterpret_cast<T *>(buf);
+  const T *s = reinterpret_cast<const T *>(src) + ((size_t)(tile_base + idx0) * cpe + c);
+  const uint16_t *sr = srank + idx0;
 #pragma unroll
-    for (int b = 0; b < BATCH; b++)
-      if (FULL || idx0 + (r0 + b) * 32 < n_valid) stage[sr[(r0 + b) * 32]] = v[b];
-  }
-  __syncthreads();
+  for (int r = 0; r < IPT; r++)
+    if (FULL || idx0 + r * 32 < n_valid) stage[sr[r * 32]] = s[(size_t)(r * 32) * cpe];
+}
+
+// goff[k] is the destination element index of staged slot tid + k*THREADS (computed once per tile,
+// shared by all streams): consecutive threads write consecutive addresses of each bucket.
+template <typename T, int THREADS, int IPT, bool FULL>
+__device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const int64_t (&goff)[IPT], int n_valid,
+                                          uint32_t cpe, uint32_t c) {
+  const T *stage = reinterpret_cast<const T *>(buf);
+  T *d = reinterpret_cast<T *>(dst) + c;
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     const int i = threadIdx.x + k * THREADS;
@@ -372,46 +389,15 @@ __device__ __forceinline__ void move_chunks_t(const unsigned char *src, unsigned
   }
 }
 
-template <typename T, int THREADS, int IPT, bool FULL>
-__device__ __forceinline__ void move_chunks(const unsigned char *src, unsigned char *dst, unsigned char *stage_raw,
-                                            const uint16_t *srank, const int64_t (&goff)[IPT], int64_t tile_base,
-                                            int n_valid, uint32_t cpe, uint32_t c, int warp, int lane) {
-  if (cpe == 1)
-    move_chunks_t<T, THREADS, IPT, FULL, true>(src, dst, stage_raw, srank, goff, tile_base, n_valid, 1, 0, warp, lane);
-  else
-    move_chunks_t<T, THREADS, IPT, FULL, false>(src, dst, stage_raw, srank, goff, tile_base, n_valid, cpe, c, warp, lane);
-}
-
-// Direct scatter of one chunk column of one stream: item r of this thread (tile index idx0 + 32 r) goes to
-// element g[r] of the destination.
-template <typename T, int IPT, bool FULL>
-__device__ __forceinline__ void direct_chunks(const unsigned char *src, unsigned char *dst, const int64_t (&g)[IPT],
-                                              int64_t first_item, int idx0, int n_valid, uint32_t cpe, uint32_t c) {
-  const T *s = reinterpret_cast<const T *>(src) + ((size_t)first_item * cpe + c);
-  T *d = reinterpret_cast<T *>(dst) + c;
-  constexpr int BATCH_MAX = sizeof(T) == 16 ? 4 : 8;
-  constexpr int BATCH = BATCH_MAX < IPT ? BATCH_MAX : IPT;
-#pragma unroll
-  for (int r0 = 0; r0 < IPT; r0 += BATCH) {
-    T v[BATCH];
-#pragma unroll
-    for (int b = 0; b < BATCH; b++)
-      if (FULL || idx0 + (r0 + b) * 32 < n_valid) v[b] = s[(size_t)((r0 + b) * 32) * cpe];
-#pragma unroll
-    for (int b = 0; b < BATCH; b++)
-      if (FULL || idx0 + (r0 + b) * 32 < n_valid) d[(size_t)g[r0 + b] * cpe] = v[b];
-  }
-}
-
-template <int KB, int THREADS, int IPT, int MODE, bool ANYCHUNK, bool FULL>
+template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
                                            const uint32_t sel) {
   constexpr int TILE = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
   using KeyT = typename UIntOf<KB>::type;
 
-  unsigned char *stage = smem;                                                               // TILE * stage_bytes
-  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)TILE * a.stage_bytes);   // NWARPS*RADIX
+  unsigned char *stage = smem;                                                               // NSTAGE * TILE * stage_bytes
+  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)NSTAGE * TILE * a.stage_bytes);  // NWARPS*RADIX
   int64_t *gbase = reinterpret_cast<int64_t *>(warp_cnt + NWARPS * RADIX);                   // RADIX
   uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase + RADIX);                          // RADIX
   uint32_t *s_wsum = s_prefix + RADIX;                                                        // 32
@@ -498,18 +484,43 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   for (int r = 0; r < IPT; r++) {
     const uint32_t d = digit_of(r);
     rank[r] += s_prefix[d] + wc[d];
-    if (MODE != 2) sdigit[rank[r]] = (uint8_t)d;
-    if (MODE == 0) srank[idx0 + r * 32] = (uint16_t)rank[r];  // payload streams pick their slot up from here
+    sdigit[rank[r]] = (uint8_t)d;
+    srank[idx0 + r * 32] = (uint16_t)rank[r];  // payload streams pick their slot up from here
   }
 
-  // ---- keys into the staging buffer (SoA: they are already in registers) ---------------------------------
+  // ---- the column pipeline.  Column 0 is the key array itself (SoA: staged from registers) or the first
+  //      column of the record (AoS); columns are staged NSTAGE deep so that the loads of the next column
+  //      overlap the look-back and the write-out of the current one. ------------------------------------------
   const bool soa_keys = key_stride == KB;
-  if (MODE != 2 && soa_keys) {
-    KeyT *kst = reinterpret_cast<KeyT *>(stage);
+  unsigned char *bufs[2] = {stage, stage + (NSTAGE == 2 ? (size_t)TILE * a.stage_bytes : 0)};
+  int is_s = soa_keys ? 1 : 0;  // issue cursor: next column to stage = chunk is_c of stream is_s
+  uint32_t is_c = 0;
+  auto issue_next = [&](unsigned char *buf) -> bool {
+    if (is_s >= a.ss.n_streams) return false;
+    const Stream &st = a.ss.streams[is_s];
+    const unsigned char *src = st.buf[sel];
+    const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
+    if (cb == 8) stage_async<8, IPT, FULL>(src, buf, srank, tile_base, idx0, n_valid, cpe, is_c);
+    else if (cb == 4) stage_async<4, IPT, FULL>(src, buf, srank, tile_base, idx0, n_valid, cpe, is_c);
+    else if (cb == 16) stage_async<16, IPT, FULL>(src, buf, srank, tile_base, idx0, n_valid, cpe, is_c);
+    else if constexpr (ANYCHUNK) {
+      if (cb == 2) stage_sync<uint16_t, IPT, FULL>(src, buf, srank, tile_base, idx0, n_valid, cpe, is_c);
+      else stage_sync<uint8_t, IPT, FULL>(src, buf, srank, tile_base, idx0, n_valid, cpe, is_c);
+    }
+    cp_async_commit();
+    if (++is_c == cpe) { is_c = 0; is_s++; }
+    return true;
+  };
+  if (soa_keys) {
+    KeyT *kst = reinterpret_cast<KeyT *>(bufs[0]);
 #pragma unroll
     for (int r = 0; r < IPT; r++)
       if (FULL || idx0 + r * 32 < n_valid) kst[rank[r]] = raw[r];
+  } else {
+    issue_next(bufs[0]);
   }
+  bool have_next = false;               // column j+1 already issued into the other buffer
+  if (NSTAGE == 2) have_next = issue_next(bufs[1]);
 
   // ---- decoupled look-back (one thread per digit), after the staging stores so that the predecessors
   //      have had time to publish.  LB_BATCH predecessors are polled per round trip: the chain of
@@ -546,90 +557,48 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     }
     gbase[tid] = (int64_t)excl - (int64_t)s_prefix[tid];
   }
-  __syncthreads();  // staged keys, sdigit and gbase visible
+  if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
+  __syncthreads();  // column 0, sdigit and gbase visible to everyone
 
-  if constexpr (MODE != 0) {
-    // ---- direct scatter: every item goes from registers straight to its final address.  The writes of
-    //      one warp instruction fall into up to 32 different buckets; the 126 MB L2 merges the partial
-    //      sectors of neighbouring tiles before they reach HBM (ncu: dram bytes ~ algorithmic bytes). ----
-    int64_t g[IPT];
-#pragma unroll
-    for (int r = 0; r < IPT; r++) g[r] = gbase[digit_of(r)] + rank[r];
-    int first_stream = 0;
-    if (soa_keys) {
-      KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
-      if (MODE == 2) {
-#pragma unroll
-        for (int r = 0; r < IPT; r++)
-          if (FULL || idx0 + r * 32 < n_valid) kdst[g[r]] = raw[r];
-      } else {
-        const KeyT *kst = reinterpret_cast<const KeyT *>(stage);
-#pragma unroll
-        for (int k = 0; k < IPT; k++) {
-          const int i = tid + k * THREADS;
-          if (FULL || i < n_valid) kdst[gbase[sdigit[i]] + i] = kst[i];
-        }
-      }
-      first_stream = 1;
-    }
-    for (int s = first_stream; s < a.ss.n_streams; s++) {
-      const Stream &st = a.ss.streams[s];
-      const unsigned char *src = st.buf[sel];
-      unsigned char *dst = st.buf[sel ^ 1];
-      const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
-      for (uint32_t c = 0; c < cpe; c++) {
-        if (cb == 8) direct_chunks<uint64_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
-        else if (cb == 4) direct_chunks<uint32_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
-        else if (cb == 16) direct_chunks<uint4, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
-        else if constexpr (ANYCHUNK) {
-          if (cb == 2) direct_chunks<uint16_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
-          else direct_chunks<uint8_t, IPT, FULL>(src, dst, g, tile_base + idx0, idx0, n_valid, cpe, c);
-        }
-      }
-    }
-    return;
-  } else {
   int64_t goff[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     const int i = tid + k * THREADS;
     goff[k] = (FULL || i < n_valid) ? gbase[sdigit[i]] + i : 0;
   }
-  int first_stream = 0;
-  if (soa_keys) {
-    const KeyT *kst = reinterpret_cast<const KeyT *>(stage);
-    KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
-#pragma unroll
-    for (int k = 0; k < IPT; k++) {
-      const int i = tid + k * THREADS;
-      if (FULL || i < n_valid) kdst[goff[k]] = kst[i];
+  int wr_s = 0;  // write cursor
+  uint32_t wr_c = 0;
+  for (int j = 0;; j++) {
+    {
+      const Stream &st = a.ss.streams[wr_s];
+      unsigned char *dst = st.buf[sel ^ 1];
+      const unsigned char *buf = bufs[NSTAGE == 2 ? (j & 1) : 0];
+      const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
+      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
+      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
+      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
+      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
+      else write_out<uint8_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
+      if (++wr_c == cpe) { wr_c = 0; wr_s++; }
     }
-    first_stream = 1;
-  }
-  // ---- every other stream (and, for AoS, every column of the record) ------------------------------------
-  for (int s = first_stream; s < a.ss.n_streams; s++) {
-    const Stream &st = a.ss.streams[s];
-    const unsigned char *src = st.buf[sel];
-    unsigned char *dst = st.buf[sel ^ 1];
-    for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
-      __syncthreads();  // previous use of the staging buffer is over
-      const uint32_t cb = st.chunk_bytes;
-      if (cb == 8) move_chunks<uint64_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-      else if (cb == 4) move_chunks<uint32_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-      else if (cb == 16) move_chunks<uint4, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-      else if constexpr (ANYCHUNK) {
-        if (cb == 2) move_chunks<uint16_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-        else move_chunks<uint8_t, THREADS, IPT, FULL>(src, dst, stage, srank, goff, tile_base, n_valid, st.chunks_per_elem, c, warp, lane);
-      }
+    if (wr_s >= a.ss.n_streams) break;
+    if (NSTAGE == 2) {
+      cp_async_wait<0>();   // my part of column j+1 has landed
+      __syncthreads();      // everyone is done writing column j out, and column j+1 is complete
+      issue_next(bufs[j & 1]);  // column j+2 into the buffer column j just vacated
+    } else {
+      __syncthreads();      // everyone is done with the staging buffer
+      issue_next(bufs[0]);
+      cp_async_wait<0>();
+      __syncthreads();
     }
-  }
   }
 }
 
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
 // ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
 // far more registers per thread, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, int MINB, int MODE, bool ANYCHUNK>
+template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
@@ -638,7 +607,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   const uint32_t sel = a.plan->src_sel[a.pass];
 
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * a.stage_bytes);
+  uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * TILE * a.stage_bytes);
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
   for (int i = threadIdx.x; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
@@ -646,9 +615,9 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
   if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, MODE, ANYCHUNK, true>(a, smem, tile, TILE, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, true>(a, smem, tile, TILE, sel);
   else
-    sweep_tile<KB, THREADS, IPT, MODE, ANYCHUNK, false>(a, smem, tile, (int)remaining, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, false>(a, smem, tile, (int)remaining, sel);
 }
 
 // ------------------------------------------------------------------------------------------------

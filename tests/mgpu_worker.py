@@ -1,0 +1,79 @@
+"""Worker of tests/test_gpu_mgpu.py: one process per GPU (torchrun), sorts sharded records with
+b200sort_mgpu_sort_soa and checks the distributed result against numpy on rank 0."""
+import ctypes
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import oracle_lib as O  # noqa: E402
+import simd_radix_sort_b200 as S  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    L = S.lib()
+    uid = [None]
+    if rank == 0:
+        buf = (ctypes.c_ubyte * 128)()
+        assert L.b200sort_mgpu_unique_id(buf) == 0, L.b200sort_last_error()
+        uid[0] = bytes(buf)
+    dist.broadcast_object_list(uid, src=0)
+    comm = ctypes.c_void_p()
+    assert L.b200sort_mgpu_comm_create(ctypes.byref(comm), world, rank, (ctypes.c_ubyte * 128).from_buffer_copy(uid[0])) == 0, \
+        L.b200sort_last_error()
+
+    cases = [(np.uint64, "Uniform", True, 1_000_003), (np.float32, "Gaussian", False, 400_000), (np.int16, "Uniform", True, 250_000),
+             (np.int64, "Gaussian", True, 300_000), (np.float64, "Uniform", False, 2_000_000)]
+    for ci, (dt, distname, up, n_local) in enumerate(cases):
+        n_local += 1000 * rank
+        keys = O.make_keys(distname, dt, n_local, seed=100 * ci + rank)
+        pay = (np.arange(n_local, dtype=np.uint64) + (rank << 40))
+        cap = int(n_local * 1.5) + 4096
+        k = torch.zeros(cap, dtype=torch.from_numpy(keys[:1]).dtype, device=dev)
+        p = torch.zeros(cap, dtype=torch.uint64, device=dev)
+        k[:n_local].copy_(torch.from_numpy(keys))
+        p[:n_local].copy_(torch.from_numpy(pay))
+        ptrs = (ctypes.c_void_p * 1)(p.data_ptr())
+        sizes = (ctypes.c_uint32 * 1)(8)
+        got = ctypes.c_int64(0)
+        rc = L.b200sort_mgpu_sort_soa(comm, k.data_ptr(), S.KEY_TYPES[np.dtype(dt).name], n_local, cap, int(up), 1, ptrs, sizes,
+                                      ctypes.byref(got), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, L.b200sort_last_error()
+        torch.cuda.synchronize()
+        m = got.value
+        out_k, out_p = k[:m].cpu().numpy(), p[:m].cpu().numpy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (keys, pay, out_k, out_p))
+        if rank == 0:
+            all_in_k = np.concatenate([g[0] for g in gathered])
+            all_in_p = np.concatenate([g[1] for g in gathered])
+            all_out_k = np.concatenate([g[2] for g in gathered])
+            all_out_p = np.concatenate([g[3] for g in gathered])
+            want = O.total_order_sorted_keys(all_in_k, up)
+            assert all_out_k.tobytes() == want.tobytes(), f"case {ci}: distributed key sequence differs"
+            # payload followed its key: payload encodes (source rank, source index)
+            src_rank, src_idx = all_out_p >> np.uint64(40), all_out_p & np.uint64((1 << 40) - 1)
+            offs = np.cumsum([0] + [len(g[0]) for g in gathered])[:-1]
+            pos = offs[src_rank.astype(np.int64)] + src_idx.astype(np.int64)
+            assert all_in_k[pos].tobytes() == all_out_k.tobytes(), f"case {ci}: payload did not follow its key"
+            assert np.array_equal(np.sort(pos), np.arange(len(all_in_k))), f"case {ci}: not a permutation"
+            sizes_out = [len(g[2]) for g in gathered]
+            assert max(sizes_out) <= 1.3 * (sum(sizes_out) / world) + 70000, f"case {ci}: unbalanced {sizes_out}"
+    dist.barrier()
+    assert L.b200sort_mgpu_comm_destroy(comm) == 0
+    dist.destroy_process_group()
+    print(f"MGPU_GPU_OK {rank}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
