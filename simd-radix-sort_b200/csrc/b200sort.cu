@@ -108,7 +108,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
 struct TileCfg { int threads, ipt; };
-static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {512, 8}, {256, 8}, {256, 16}, {256, 8}};
+static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {256, 8}, {256, 16}};
 static constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 
 static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1) {
@@ -135,10 +135,16 @@ static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t sm
   if (nstage != 1 && nstage != 2)
     nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * MINB <= smem_optin + 1024) ? 2 : 1;
   if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2) > smem_optin) nstage = 1;
-  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage);
   void (*k)(const SweepArgs);
-  if (nstage == 2) k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false>;
-  else k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false>;
+  if (a.lut != nullptr) {  // multi-GPU partition pass: one generic instantiation
+    nstage = 1;
+    k = onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true>;
+  } else if (nstage == 2) {
+    k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false, false>;
+  } else {
+    k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false>;
+  }
+  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
@@ -152,10 +158,8 @@ static cudaError_t launch_sweep_kb(int cfg, const SweepArgs &a, int64_t n_tiles,
   switch (cfg) {
     case 0: return launch_sweep_t<KB, 512, 16, 1>(a, n_tiles, smem, mode, st);
     case 1: return launch_sweep_t<KB, 256, 16, 3>(a, n_tiles, smem, mode, st);
-    case 2: return launch_sweep_t<KB, 512, 8, 2>(a, n_tiles, smem, mode, st);
-    case 3: return launch_sweep_t<KB, 256, 8, 4>(a, n_tiles, smem, mode, st);
-    case 4: return launch_sweep_t<KB, 256, 16, 2>(a, n_tiles, smem, mode, st);
-    default: return launch_sweep_t<KB, 256, 8, 3>(a, n_tiles, smem, mode, st);
+    case 2: return launch_sweep_t<KB, 256, 8, 4>(a, n_tiles, smem, mode, st);
+    default: return launch_sweep_t<KB, 256, 16, 4>(a, n_tiles, smem, mode, st);
   }
 }
 

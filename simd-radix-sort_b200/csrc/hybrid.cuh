@@ -38,19 +38,25 @@ struct SegfixArgs {
   HybridCtrl *ctrl;
 };
 
+// Moves the queued elements of one chunk column: entry i goes from window position q_p[i] to q_d[i].
+// Source and destination may be the same array, so everything is read before anything is written.
 template <typename T>
-__device__ __forceinline__ void segfix_move(const unsigned char *src, unsigned char *dst, int64_t w0, const int (&dest)[SF_PPT],
-                                            uint32_t active, uint32_t cpe, uint32_t c) {
-  const T *s = reinterpret_cast<const T *>(src);
-  T *d = reinterpret_cast<T *>(dst);
+__device__ __forceinline__ void segfix_move(const unsigned char *src, unsigned char *dst, int64_t w0, const uint16_t *q_p,
+                                            const uint16_t *q_d, int count, uint32_t cpe, uint32_t c) {
+  const T *s = reinterpret_cast<const T *>(src) + (size_t)w0 * cpe + c;
+  T *d = reinterpret_cast<T *>(dst) + (size_t)w0 * cpe + c;
   T v[SF_PPT];
 #pragma unroll
-  for (int k = 0; k < SF_PPT; k++)
-    if ((active >> k) & 1) v[k] = s[(size_t)(w0 + threadIdx.x + k * SF_THREADS) * cpe + c];
-  __syncthreads();  // source and destination may be the same array: read everything before writing
+  for (int j = 0; j < SF_PPT; j++) {
+    const int i = threadIdx.x + j * SF_THREADS;
+    if (i < count) v[j] = s[(size_t)q_p[i] * cpe];
+  }
+  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < SF_PPT; k++)
-    if ((active >> k) & 1) d[(size_t)(w0 + dest[k]) * cpe + c] = v[k];
+  for (int j = 0; j < SF_PPT; j++) {
+    const int i = threadIdx.x + j * SF_THREADS;
+    if (i < count) d[(size_t)q_d[i] * cpe] = v[j];
+  }
 }
 
 template <int KB, bool ANYCHUNK>
@@ -103,74 +109,85 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
   auto seg_start = [&](int p) -> int {
     int w = p >> 5;
     uint32_t m = hbits[w] & (0xffffffffu >> (31 - (p & 31)));
-    for (int s = 0; m == 0 && w > 0 && s < MAXWORDS; s++) m = hbits[--w];
+    if (m == 0)
+      for (int s = 0; m == 0 && w > 0 && s < MAXWORDS; s++) m = hbits[--w];
     return m ? (w << 5) + 31 - __clz(m) : -1;
   };
   // end of the segment holding p: the nearest head after p (SF_BIG: none within SF_MAXSEG)
   auto seg_end = [&](int p) -> int {
     int w = p >> 5;
-    uint32_t m = (p & 31) == 31 ? 0u : (hbits[w] & (0xffffffffu << ((p & 31) + 1)));
-    for (int s = 0; m == 0 && w < SF_W / 32 && s < MAXWORDS; s++) m = hbits[++w];
+    uint32_t m = hbits[w] & ~(0xffffffffu >> (31 - (p & 31)));  // bits above p
+    if (m == 0)
+      for (int s = 0; m == 0 && w < SF_W / 32 && s < MAXWORDS; s++) m = hbits[++w];
     return m ? (w << 5) + __ffs(m) - 1 : SF_BIG;
   };
 
-  // ---- classify every position this thread moves; rank inside short segments ---------------------------
-  int dest[SF_PPT];
-  uint32_t active = 0;
+  // ---- classify every window position; rank inside short segments; queue what has to move --------------
+  __shared__ uint16_t q_p[SF_W];
+  __shared__ uint16_t q_d[SF_W];
+  __shared__ int q_n;
+  if (tid == 0) q_n = 0;
+  __syncthreads();
+  const int off_s = (int)(s0 - w0), off_e = (int)(e0 - w0);  // this tile's own positions inside the window
   bool fail = false;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < SF_PPT; k++) {
     const int p = tid + k * SF_THREADS;
-    dest[k] = p;
+    int dest = p;
+    bool act = false;
     if (p < wn) {
       const int st = seg_start(p), en = seg_end(p);
-      const int64_t gp = w0 + p;
       const bool is_long = st < 0 || en == SF_BIG || (en - st) > SF_MAXSEG;
       if (is_long) {
         // long segments stay as they are (and must consist of one repeated key); the tile that owns the
-        // position copies it
-        if (gp >= s0 && gp < e0) {
-          active |= 1u << k;
+        // position copies it when the data still sits in the shadow
+        if (p >= off_s && p < off_e) {
+          act = sel != 0;
           if (p > 0 && !is_head(p) && wkey[p] != wkey[p - 1]) fail = true;
         }
-      } else {
-        const int64_t gh = w0 + st;
-        if (gh >= s0 && gh < e0) {  // the tile holding a segment's head orders the whole segment
-          active |= 1u << k;
-          if (en - st > 1) {
-            const O mine = wkey[p];
-            int cnt = 0;
-            for (int q = st; q < en; q++) {
-              const O o = wkey[q];
-              cnt += (o < mine || (o == mine && q < p)) ? 1 : 0;
-            }
-            dest[k] = st + cnt;
+      } else if (st >= off_s && st < off_e) {  // the tile holding a segment's head orders the whole segment
+        if (en - st > 1) {
+          const O mine = wkey[p];
+          int cnt = 0;
+          for (int q = st; q < en; q++) {
+            const O o = wkey[q];
+            cnt += (o < mine || (o == mine && q < p)) ? 1 : 0;
           }
+          dest = st + cnt;
         }
+        act = sel != 0 || dest != p;  // in place only displaced elements move
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&q_n, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (act) {
+        const int i = base + __popc(m & lanemask_lt());
+        q_p[i] = (uint16_t)p;
+        q_d[i] = (uint16_t)dest;
       }
     }
   }
   if (__any_sync(0xffffffffu, fail) && lane == 0) atomicOr(&a.ctrl->flags[0], 1u);
-  if (sel == 0) {
-    // the swept data already lies in the caller's arrays: only displaced elements have to move
-#pragma unroll
-    for (int k = 0; k < SF_PPT; k++)
-      if (dest[k] == tid + k * SF_THREADS) active &= ~(1u << k);
-  }
+  __syncthreads();
+  const int count = q_n;
+  if (count == 0) return;
 
-  // ---- move every stream: window position p -> dest (side `sel` -> side 0) ----------------------------------
+  // ---- move every stream: window position q_p -> q_d (side `sel` -> side 0) -------------------------------
   for (int s = 0; s < a.ss.n_streams; s++) {
     const Stream &st = a.ss.streams[s];
     const unsigned char *src = st.buf[sel];
     unsigned char *dst = st.buf[0];
     for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
       const uint32_t cb = st.chunk_bytes;
-      if (cb == 8) segfix_move<uint64_t>(src, dst, w0, dest, active, st.chunks_per_elem, c);
-      else if (cb == 4) segfix_move<uint32_t>(src, dst, w0, dest, active, st.chunks_per_elem, c);
-      else if (cb == 16) segfix_move<uint4>(src, dst, w0, dest, active, st.chunks_per_elem, c);
+      if (cb == 8) segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
+      else if (cb == 4) segfix_move<uint32_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
+      else if (cb == 16) segfix_move<uint4>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
       else if constexpr (ANYCHUNK) {
-        if (cb == 2) segfix_move<uint16_t>(src, dst, w0, dest, active, st.chunks_per_elem, c);
-        else segfix_move<uint8_t>(src, dst, w0, dest, active, st.chunks_per_elem, c);
+        if (cb == 2) segfix_move<uint16_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
+        else segfix_move<uint8_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
       }
     }
   }

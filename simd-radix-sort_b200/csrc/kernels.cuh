@@ -359,9 +359,15 @@ __device__ __forceinline__ void stage_async(const unsigned char *src, unsigned c
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(buf);
   const unsigned char *s = src + ((size_t)(tile_base + idx0) * cpe + c) * CB;
   const uint16_t *sr = srank + idx0;
+  if (cpe == 1) {
 #pragma unroll
-  for (int r = 0; r < IPT; r++)
-    if (FULL || idx0 + r * 32 < n_valid) cp_async<CB>(base + (uint32_t)sr[r * 32] * CB, s + (size_t)(r * 32) * cpe * CB);
+    for (int r = 0; r < IPT; r++)
+      if (FULL || idx0 + r * 32 < n_valid) cp_async<CB>(base + (uint32_t)sr[r * 32] * CB, s + (size_t)(r * 32) * CB);
+  } else {
+#pragma unroll
+    for (int r = 0; r < IPT; r++)
+      if (FULL || idx0 + r * 32 < n_valid) cp_async<CB>(base + (uint32_t)sr[r * 32] * CB, s + (size_t)(r * 32) * cpe * CB);
+  }
 }
 
 template <typename T, int IPT, bool FULL>
@@ -380,16 +386,20 @@ __device__ __forceinline__ void stage_sync(const unsigned char *src, unsigned ch
 template <typename T, int THREADS, int IPT, bool FULL>
 __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const int64_t (&goff)[IPT], int n_valid,
                                           uint32_t cpe, uint32_t c) {
-  const T *stage = reinterpret_cast<const T *>(buf);
+  const T *stage = reinterpret_cast<const T *>(buf) + threadIdx.x;
   T *d = reinterpret_cast<T *>(dst) + c;
+  if (cpe == 1) {  // one chunk per element (the common shapes): no index multiply
 #pragma unroll
-  for (int k = 0; k < IPT; k++) {
-    const int i = threadIdx.x + k * THREADS;
-    if (FULL || i < n_valid) d[(size_t)goff[k] * cpe] = stage[i];
+    for (int k = 0; k < IPT; k++)
+      if (FULL || (int)threadIdx.x + k * THREADS < n_valid) d[goff[k]] = stage[k * THREADS];
+  } else {
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+      if (FULL || (int)threadIdx.x + k * THREADS < n_valid) d[(size_t)goff[k] * cpe] = stage[k * THREADS];
   }
 }
 
-template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool FULL>
+template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
                                            const uint32_t sel) {
   constexpr int TILE = THREADS * IPT;
@@ -419,11 +429,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     raw[r] = (FULL || idx0 + r * 32 < n_valid) ? *reinterpret_cast<const KeyT *>(kp + (size_t)(r * 32) * key_stride) : (KeyT)0;
   // The digit of item r is recomputed where it is needed instead of being kept in IPT registers.
   const DigitX dx = make_digitx(a.ko, a.shift);
-  const bool use_lut = a.lut != nullptr;
   auto digit_of = [&](int r) -> uint32_t {
     // padding of the last tile ranks behind everything (digit 255, last in index order)
     if (!FULL && idx0 + r * 32 >= n_valid) return RADIX - 1;
-    return use_lut ? lut_digit<KB>(raw[r], a) : fast_digit<KB>(raw[r], dx);
+    if constexpr (LUT) return lut_digit<KB>(raw[r], a);  // multi-GPU partition pass
+    else return fast_digit<KB>(raw[r], dx);
   };
 
   // ---- rank inside the warp (stable) -----------------------------------------------------------------
@@ -598,7 +608,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
 // ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
 // far more registers per thread, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK>
+template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
@@ -615,9 +625,9 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
   if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, true>(a, smem, tile, TILE, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, true>(a, smem, tile, TILE, sel);
   else
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, false>(a, smem, tile, (int)remaining, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, false>(a, smem, tile, (int)remaining, sel);
 }
 
 // ------------------------------------------------------------------------------------------------
