@@ -119,7 +119,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -310,6 +310,8 @@ def main():
     e2e = None
     h2d = d2h = n * RECORD_BYTES
     try:
+        if args.e2e_steps <= 0:
+            raise RuntimeError("skipped (--e2e-steps 0)")
         hk = torch.empty(n, dtype=torch.uint64, pin_memory=True)
         hp = torch.empty(n, dtype=torch.uint64, pin_memory=True)
         e2e_ms = []
@@ -374,7 +376,7 @@ def main():
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only) ----
     cpu = None
-    if not multi:
+    if not multi and args.cpu_sample > 0:
         dt, kind, sample, cores, used_n = cpu_sort_sample(args.cpu_sample)
         cpu = {"value": used_n / dt * 1e-9, "unit": "Gpairs/s", "cores": cores, "kind": kind, "sample": sample}
 

@@ -16,8 +16,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb200sort.so"
-SOURCES = [CSRC / "b200sort.cu"]
-HEADERS = [CSRC / "kernels.cuh", CSRC / "hybrid.cuh", CSRC / "mgpu.cuh", PKG.parent / "include" / "b200sort.h"]
+SOURCES = [CSRC / "b200sort.cu"] + [CSRC / f"sweep_kb{k}.cu" for k in (1, 2, 4, 8)]
+HEADERS = [CSRC / "kernels.cuh", CSRC / "hybrid.cuh", CSRC / "mgpu.cuh", CSRC / "sweep_select.cuh", PKG.parent / "include" / "b200sort.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
@@ -40,15 +40,37 @@ def needs_build() -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
+    """Compiles every translation unit for sm_100a (in parallel) and links libb200sort.so."""
     if not force and not needs_build():
         return LIB
-    srcs = [str(s) for s in SOURCES if s.exists()]
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *srcs, "-ldl"]
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    newest_header = max(h.stat().st_mtime for h in HEADERS if h.exists())
+
+    def compile_one(src: Path) -> Path:
+        obj = objdir / (src.stem + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_header):
+            return obj
+        cmd = [nvcc_path(), *compile_flags, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, [s for s in SOURCES if s.exists()]))
+    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
+           *[str(o) for o in objs], "-ldl"]
     if verbose:
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "sweep_select.cuh"
 #include "hybrid.cuh"
 
 namespace b200sort {
@@ -107,93 +108,74 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
-struct TileCfg { int threads, ipt; };
-static constexpr TileCfg kTileCfgs[] = {{512, 16}, {256, 16}, {256, 8}, {256, 16}};
-static constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
-
 static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1) {
   const size_t tile = (size_t)c.threads * c.ipt;
-  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3;
+  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 + RADIX * 4;
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
 
-template <int KB, int THREADS, int IPT, int MINB>
-static cudaError_t launch_sweep_t(const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int mode, cudaStream_t st) {
+static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int mode, cudaStream_t st) {
   (void)mode;
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   int n_cols = 0;
-  const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == KB;
+  const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == (uint32_t)kb;
   for (int s = soa ? 1 : 0; s < a.ss.n_streams; s++) {
     any = any || a.ss.streams[s].chunk_bytes < 4;
     n_cols += (int)a.ss.streams[s].chunks_per_elem;
   }
   n_cols += soa ? 1 : 0;
-  const TileCfg tc{THREADS, IPT};
-  // double-buffer the columns when there is more than one and MINB CTAs still fit on an SM
+  const TileCfg tc = kTileCfgs[cfg];
+  // double-buffer the columns when there is more than one and minb CTAs still fit on an SM
   int nstage = (int)opt_nstage.load();
   if (nstage != 1 && nstage != 2)
-    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * MINB <= smem_optin + 1024) ? 2 : 1;
+    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * tc.minb <= smem_optin + 1024) ? 2 : 1;
   if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2) > smem_optin) nstage = 1;
-  void (*k)(const SweepArgs);
-  if (a.lut != nullptr) {  // multi-GPU partition pass: one generic instantiation
-    nstage = 1;
-    k = onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true>;
-  } else if (nstage == 2) {
-    k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false, false>;
-  } else {
-    k = any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false>;
+  const bool lut = a.lut != nullptr;
+  if (lut) nstage = 1;
+  SweepFn k;
+  switch (kb) {
+    case 1: k = sweep_fn_kb1(cfg, nstage, any, lut); break;
+    case 2: k = sweep_fn_kb2(cfg, nstage, any, lut); break;
+    case 4: k = sweep_fn_kb4(cfg, nstage, any, lut); break;
+    default: k = sweep_fn_kb8(cfg, nstage, any, lut); break;
   }
   const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
-  k<<<(unsigned)n_tiles, THREADS, smem, st>>>(a);
+  k<<<(unsigned)n_tiles, tc.threads, smem, st>>>(a);
   g_launches++;
   return cudaGetLastError();
 }
 
-template <int KB>
-static cudaError_t launch_sweep_kb(int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, int mode, cudaStream_t st) {
-  switch (cfg) {
-    case 0: return launch_sweep_t<KB, 512, 16, 1>(a, n_tiles, smem, mode, st);
-    case 1: return launch_sweep_t<KB, 256, 16, 3>(a, n_tiles, smem, mode, st);
-    case 2: return launch_sweep_t<KB, 256, 8, 4>(a, n_tiles, smem, mode, st);
-    default: return launch_sweep_t<KB, 256, 16, 4>(a, n_tiles, smem, mode, st);
-  }
-}
-
-static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem, int mode, cudaStream_t st) {
-  switch (kb) {
-    case 1: return launch_sweep_kb<1>(cfg, a, n_tiles, smem, mode, st);
-    case 2: return launch_sweep_kb<2>(cfg, a, n_tiles, smem, mode, st);
-    case 4: return launch_sweep_kb<4>(cfg, a, n_tiles, smem, mode, st);
-    default: return launch_sweep_kb<8>(cfg, a, n_tiles, smem, mode, st);
-  }
-}
-
-constexpr int HIST_THREADS = 512, HIST_IPT = 8;
+constexpr int HIST_THREADS = 256;  // key-only sweeps: 256 threads x NLD x 16 B per tile, 4 CTAs per SM
+constexpr int hist_nld(int kb) { return kb == 1 ? 2 : 4; }  // at most 32 keys per thread
 
 template <int KB>
-static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, cudaStream_t st) {
+static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, bool probe, cudaStream_t st) {
   ProfScope ps(PK_HIST, st);
-  if (use_match)
-    hist_kernel<KB, HIST_THREADS, HIST_IPT, true><<<grid, HIST_THREADS, 0, st>>>(a);
-  else
-    hist_kernel<KB, HIST_THREADS, HIST_IPT, false><<<grid, HIST_THREADS, 0, st>>>(a);
+  if (probe) {
+    if (use_match) probe_kernel<KB, HIST_THREADS, hist_nld(KB), true><<<grid, HIST_THREADS, 0, st>>>(a);
+    else probe_kernel<KB, HIST_THREADS, hist_nld(KB), false><<<grid, HIST_THREADS, 0, st>>>(a);
+  } else {
+    if (use_match) hist_kernel<KB, HIST_THREADS, hist_nld(KB), true><<<grid, HIST_THREADS, 0, st>>>(a);
+    else hist_kernel<KB, HIST_THREADS, hist_nld(KB), false><<<grid, HIST_THREADS, 0, st>>>(a);
+  }
   g_launches++;
   return cudaGetLastError();
 }
 
-cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, cudaStream_t st) {
-  const int64_t tiles = (a.n + HIST_THREADS * HIST_IPT - 1) / (HIST_THREADS * HIST_IPT);
-  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * 4);
+cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, bool probe, cudaStream_t st) {
+  const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
+  const int64_t tiles = (a.n + tile_keys - 1) / tile_keys;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * 8);
   const bool m = opt_hist_match.load() != 0;
   switch (kb) {
-    case 1: return launch_hist_t<1>(a, grid, m, st);
-    case 2: return launch_hist_t<2>(a, grid, m, st);
-    case 4: return launch_hist_t<4>(a, grid, m, st);
-    default: return launch_hist_t<8>(a, grid, m, st);
+    case 1: return launch_hist_t<1>(a, grid, m, probe, st);
+    case 2: return launch_hist_t<2>(a, grid, m, probe, st);
+    case 4: return launch_hist_t<4>(a, grid, m, probe, st);
+    default: return launch_hist_t<8>(a, grid, m, probe, st);
   }
 }
 
@@ -252,7 +234,7 @@ struct StreamDesc { void *ptr; uint32_t elem_bytes; };
 struct Layout {
   size_t shadow_off[MAX_STREAMS];
   size_t ctrl_off, ctrl_bytes;       // zeroed at the start of every sort
-  size_t ghist_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off;
+  size_t ghist_off, ghist2_off, probe_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off;
   size_t total;
   int64_t n_tiles;
 };
@@ -274,7 +256,9 @@ static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int t
   L->n_tiles = (n + tile - 1) / tile;
   // hybrid path tiles may be smaller than the sweep tiles; size the look-back for the smallest tile used
   L->ctrl_off = off;
-  L->ghist_off = off;               off += (size_t)8 * RADIX * 8;
+  L->ghist_off = off;               off += (size_t)8 * RADIX * 8;   // sampled histograms (probe)
+  L->ghist2_off = off;              off += (size_t)8 * RADIX * 8;   // exact histograms, one digit position at a time
+  L->probe_off = off;               off += 64;
   L->tilectr_off = off;             off += MAX_PASSES * 4;
   L->plan_off = off;                off = align_up(off + sizeof(Plan), 256);
   L->hyb_off = off;                 off = align_up(off + sizeof(HybridCtrl), 256);
@@ -336,7 +320,6 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   uint64_t *ghist = (uint64_t *)(ws + L.ghist_off);
   uint32_t *tile_counter = (uint32_t *)(ws + L.tilectr_off);
   Plan *plan = (Plan *)(ws + L.plan_off);
-  uint64_t *bin_base = (uint64_t *)(ws + L.binbase_off);
   uint64_t *lookback = (uint64_t *)(ws + L.lookback_off);
 
   const uint64_t launches_before = g_launches.load();
@@ -359,15 +342,20 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   {
     // ---- one histogram sweep over all digit positions, the bucket-offset scan (+ pass plan), one
     //      scatter pass per digit position (skipped ones return at once), segment finish, copy-back ----
+    uint64_t *ghist_exact = (uint64_t *)(ws + L.ghist2_off);
+    ProbeOut *probe = (ProbeOut *)(ws + L.probe_off);
     HistArgs ha{};
     ha.keys = ss.streams[0].buf[0];
     ha.stride = streams[0].elem_bytes;
-    ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist;
-    CUDA_TRY(launch_hist(kb, ha, di.sm_count, stream));
+    ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
+    {
+      const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
+      ha.sample = (n / tile_keys) >= 8192 ? 16 : 1;  // entropies from 1/16 of the tiles once there are plenty
+    }
+    CUDA_TRY(launch_hist(kb, ha, di.sm_count, /*probe=*/true, stream));
 
     ScanArgs sa{};
-    sa.ghist = ghist; sa.bin_base = bin_base; sa.plan = plan; sa.n = n; sa.n_passes = kb;
-    for (int p = 0; p < kb; p++) sa.digit_of_pass[p] = p;
+    sa.ghist = ghist; sa.probe = probe; sa.plan = plan; sa.n = n; sa.n_passes = kb;
     sa.allow_skip = (int)opt_allow_skip.load();
     sa.hybrid = hybrid ? 1 : 0;
     sa.margin_bits = (float)opt_margin_bits.load();
@@ -378,11 +366,16 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 
+    // exact histogram of the first executed pass only; every pass counts its successor's digit
+    HistArgs hb = ha;
+    hb.ghist = ghist_exact; hb.plan = plan; hb.probe = nullptr;
+    CUDA_TRY(launch_hist(kb, hb, di.sm_count, /*probe=*/false, stream));
+
     const int64_t n_tiles = (n + tile - 1) / tile;
     for (int p = 0; p < kb; p++) {
       SweepArgs wa{};
       wa.ss = ss; wa.n = n; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
-      wa.bin_base = bin_base + (size_t)p * RADIX;
+      wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
       CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, 0, stream));
@@ -411,8 +404,8 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     stt.passes_planned = (uint32_t)kb;
-    stt.hist_sweeps = 1;
-    stt.algorithmic_bytes = (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
+    stt.hist_sweeps = 2;  // probe + exact histogram of the first pass
+    stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
     if (hybrid) {
       // The plan was made on the device; read it (and the fall-back flag) back.  This is the one host
       // synchronisation of the hybrid path.
@@ -424,7 +417,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       stt.passes_planned = hplan.n_exec;
       stt.segfix_passes = hplan.cut_digit != 0 ? 1 : 0;
       stt.cut_digit = hplan.cut_digit;
-      stt.algorithmic_bytes = (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
+      stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
       if (hctrl.flags[0] != 0) {
         // a long bucket with distinct keys: finish with the plain digit-by-digit path (the array is a
         // permutation of the input, already ordered by its top digits)

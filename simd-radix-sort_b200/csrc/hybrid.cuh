@@ -40,27 +40,24 @@ struct SegfixArgs {
 
 // Moves the queued elements of one chunk column: entry i goes from window position q_p[i] to q_d[i].
 // Source and destination may be the same array, so everything is read before anything is written.
+// Moves the queued elements of one chunk column: entry i goes from window position q_p[i] to q_d[i].
+// Source and destination may be the same array, so the whole column is read into shared memory (the
+// key window is no longer needed and is reused as the buffer) before anything is written.
 template <typename T>
 __device__ __forceinline__ void segfix_move(const unsigned char *src, unsigned char *dst, int64_t w0, const uint16_t *q_p,
-                                            const uint16_t *q_d, int count, uint32_t cpe, uint32_t c) {
+                                            const uint16_t *q_d, int count, uint32_t cpe, uint32_t c, void *stage_raw) {
+  static_assert(sizeof(T) <= 8, "columns wider than 8 bytes are moved as 8-byte halves");
   const T *s = reinterpret_cast<const T *>(src) + (size_t)w0 * cpe + c;
   T *d = reinterpret_cast<T *>(dst) + (size_t)w0 * cpe + c;
-  T v[SF_PPT];
-#pragma unroll
-  for (int j = 0; j < SF_PPT; j++) {
-    const int i = threadIdx.x + j * SF_THREADS;
-    if (i < count) v[j] = s[(size_t)q_p[i] * cpe];
-  }
+  T *stage = reinterpret_cast<T *>(stage_raw);
+  for (int i = threadIdx.x; i < count; i += SF_THREADS) stage[i] = s[(size_t)q_p[i] * cpe];
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < SF_PPT; j++) {
-    const int i = threadIdx.x + j * SF_THREADS;
-    if (i < count) d[(size_t)q_d[i] * cpe] = v[j];
-  }
+  for (int i = threadIdx.x; i < count; i += SF_THREADS) d[(size_t)q_d[i] * cpe] = stage[i];
+  __syncthreads();
 }
 
 template <int KB, bool ANYCHUNK>
-__global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_constant__ SegfixArgs a) {
+__global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_constant__ SegfixArgs a) {
   using O = typename OrdOf<KB>::type;
   const uint32_t cut = a.plan->cut_digit;
   if (cut == 0) return;  // every varying digit was swept: nothing to finish
@@ -130,12 +127,17 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
   __syncthreads();
   const int off_s = (int)(s0 - w0), off_e = (int)(e0 - w0);  // this tile's own positions inside the window
   bool fail = false;
-#pragma unroll 1
+#pragma unroll 2
   for (int k = 0; k < SF_PPT; k++) {
     const int p = tid + k * SF_THREADS;
     int dest = p;
     bool act = false;
-    if (p < wn) {
+    // a head directly followed by another head is a one-key bucket: nothing to order (the common case);
+    // in place it does not even have to move
+    const uint32_t two = (uint32_t)((((uint64_t)hbits[(p >> 5) + 1] << 32) | hbits[p >> 5]) >> (p & 31)) & 3u;
+    if (p < wn && two == 3u) {
+      act = sel != 0 && p >= off_s && p < off_e;
+    } else if (p < wn) {
       const int st = seg_start(p), en = seg_end(p);
       const bool is_long = st < 0 || en == SF_BIG || (en - st) > SF_MAXSEG;
       if (is_long) {
@@ -181,13 +183,15 @@ __global__ void __launch_bounds__(SF_THREADS, 2) segfix_kernel(const __grid_cons
     const unsigned char *src = st.buf[sel];
     unsigned char *dst = st.buf[0];
     for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
-      const uint32_t cb = st.chunk_bytes;
-      if (cb == 8) segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
-      else if (cb == 4) segfix_move<uint32_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
-      else if (cb == 16) segfix_move<uint4>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
-      else if constexpr (ANYCHUNK) {
-        if (cb == 2) segfix_move<uint16_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
-        else segfix_move<uint8_t>(src, dst, w0, q_p, q_d, count, st.chunks_per_elem, c);
+      const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
+      if (cb == 8) segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
+      else if (cb == 4) segfix_move<uint32_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
+      else if (cb == 16) {
+        segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, cpe * 2, c * 2, wkey);
+        segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, cpe * 2, c * 2 + 1, wkey);
+      } else if constexpr (ANYCHUNK) {
+        if (cb == 2) segfix_move<uint16_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
+        else segfix_move<uint8_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
       }
     }
   }

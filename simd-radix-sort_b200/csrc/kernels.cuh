@@ -78,6 +78,18 @@ struct Plan {
   // each run of keys that agree on all bits >= 8*cut_digit (0 = every varying digit is swept)
   uint32_t cut_digit;
   uint32_t n_const;     // digit positions on which all keys agree
+  // exact digit histograms are produced just in time: first_exec_p1 - 1 is the digit position of the
+  // first executed pass (counted by hist_kernel), next_exec_p1[p] - 1 the digit position of the pass
+  // executed after pass p (counted by pass p itself while it has the keys in registers); 0 = none
+  uint32_t first_exec_p1;
+  uint32_t next_exec_p1[MAX_PASSES];
+  uint32_t skewed[MAX_PASSES];  // digit position has a low-entropy histogram: aggregate equal digits per warp
+};
+
+// per-sort scalars produced by probe_kernel (zero-initialised by the host)
+struct ProbeOut {
+  unsigned long long or_bits;    // OR of all ordered keys
+  unsigned long long nand_bits;  // OR of the complements: a bit varies iff it is set in both words
 };
 
 // look-back status word: [63:62] flag, [61:57] generation tag, [56:0] value
@@ -129,8 +141,11 @@ struct HistArgs {
   uint32_t stride;      // bytes between consecutive keys (element size of stream 0)
   int64_t n;
   KeyOrder ko;
-  uint32_t digit_mask;  // bit p set: digit position p is counted
+  uint32_t digit_mask;  // bit p set: digit position p is counted (probe_kernel: on the sampled tiles)
   uint64_t *ghist;      // [KB][RADIX] counters, zeroed by the host
+  const Plan *plan;     // hist_kernel: when set, count exactly the digit position plan->first_exec_p1 - 1
+  ProbeOut *probe;      // probe_kernel
+  uint32_t sample;      // probe_kernel: every sample-th tile contributes to the histograms
 };
 
 // One digit of one key into the block's shared-memory counters.  Lanes of a warp that all hold the same
@@ -152,41 +167,134 @@ __device__ __forceinline__ void hist_add(uint32_t *bins, uint32_t d, unsigned vm
   }
 }
 
-template <int KB, int THREADS, int IPT, bool USE_MATCH>
-__global__ void __launch_bounds__(THREADS) hist_kernel(HistArgs a) {
+// Key loading shared by the two key-only sweeps.  Order does not matter for a histogram, so when the keys
+// are a dense, 16-byte aligned array every thread pulls NLD 16-byte vectors per tile (many bytes in
+// flight per thread; with several resident CTAs per SM this is what keeps HBM busy); otherwise (AoS
+// records, odd alignment) one key per load.
+template <int KB, int THREADS, int NLD>
+struct KeyTile {
+  using O = typename OrdOf<KB>::type;
+  static constexpr int VEC = 16 / KB;                 // keys per 16-byte vector
+  static constexpr int PER_THREAD = NLD * VEC;
+  static constexpr int TILE = THREADS * PER_THREAD;   // keys per tile
+  O u[PER_THREAD];
+  uint32_t valid;  // bit i: u[i] holds a key
+
+  __device__ __forceinline__ void load(const unsigned char *keys, uint32_t stride, int64_t n, int64_t tile, const KeyOrder &ko) {
+    using KeyT = typename UIntOf<KB>::type;
+    const int64_t base = tile * TILE;
+    valid = 0;
+    const bool dense = stride == KB && (((uintptr_t)keys) & 15) == 0;
+    if (dense && base + TILE <= n) {
+      const uint4 *v = reinterpret_cast<const uint4 *>(keys + (size_t)base * KB) + threadIdx.x;
+      uint4 q[NLD];
+#pragma unroll
+      for (int j = 0; j < NLD; j++) q[j] = v[j * THREADS];
+#pragma unroll
+      for (int j = 0; j < NLD; j++) {
+        KeyT k[VEC];
+        memcpy(k, &q[j], 16);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) u[j * VEC + e] = to_ordered<KB>(k[e], ko);
+      }
+      valid = PER_THREAD >= 32 ? 0xffffffffu : ((1u << PER_THREAD) - 1);
+    } else {
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; i++) {
+        const int64_t idx = base + (int64_t)i * THREADS + threadIdx.x;
+        if (idx < n) {
+          u[i] = to_ordered<KB>(load_key<KB>(keys, idx, stride), ko);
+          valid |= 1u << i;
+        } else {
+          u[i] = 0;
+        }
+      }
+    }
+  }
+};
+
+// K1a: probe.  One sweep over the keys that is cheap in atomics: the exact OR / AND of all ordered keys
+// (which digit positions are constant), and the histograms of every digit position on a 1/sample
+// subset of the tiles (their entropies steer the pass plan; they are never used as offsets).
+template <int KB, int THREADS, int NLD, bool USE_MATCH>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs a) {
+  using KT = KeyTile<KB, THREADS, NLD>;
   using O = typename OrdOf<KB>::type;
   __shared__ uint32_t sh[KB * RADIX];
   for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) sh[i] = 0;
   __syncthreads();
-
-  constexpr int TILE = THREADS * IPT;
-  const int64_t n_tiles = (a.n + TILE - 1) / TILE;
+  const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
+  O acc_or = 0, acc_nand = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t base = tile * TILE;
-    O u[IPT];
-    bool valid[IPT];
+    KT kt;
+    kt.load(a.keys, a.stride, a.n, tile, a.ko);
 #pragma unroll
-    for (int r = 0; r < IPT; r++) {
-      const int64_t i = base + (int64_t)r * THREADS + threadIdx.x;
-      valid[r] = i < a.n;
-      u[r] = valid[r] ? to_ordered<KB>(load_key<KB>(a.keys, i, a.stride), a.ko) : (O)0;
-    }
+    for (int i = 0; i < KT::PER_THREAD; i++)
+      if ((kt.valid >> i) & 1) { acc_or |= kt.u[i]; acc_nand |= ~kt.u[i]; }
+    if (tile % a.sample == 0) {
 #pragma unroll
-    for (int r = 0; r < IPT; r++) {
-      const unsigned vmask = __ballot_sync(0xffffffffu, valid[r]);
-      if (valid[r]) {
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const bool v = (kt.valid >> i) & 1;
+        const unsigned vmask = __ballot_sync(0xffffffffu, v);
+        if (v) {
 #pragma unroll
-        for (int p = 0; p < KB; p++) {
-          if ((a.digit_mask >> p) & 1)
-            hist_add<USE_MATCH>(&sh[p * RADIX], (uint32_t)(u[r] >> (p * RADIX_BITS)) & (RADIX - 1), vmask);
+          for (int p = 0; p < KB; p++)
+            hist_add<USE_MATCH>(&sh[p * RADIX], (uint32_t)(kt.u[i] >> (p * RADIX_BITS)) & (RADIX - 1), vmask);
         }
       }
     }
+  }
+  unsigned long long o = acc_or, na = acc_nand;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    o |= __shfl_xor_sync(0xffffffffu, o, s);
+    na |= __shfl_xor_sync(0xffffffffu, na, s);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(&a.probe->or_bits, o);
+    atomicOr(&a.probe->nand_bits, na);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) {
     const uint32_t c = sh[i];
     if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ghist[i]), (unsigned long long)c);
+  }
+}
+
+// K1b: exact histogram of ONE digit position -- the first executed pass (a.plan) -- every later pass's
+// histogram being counted by the pass before it.
+template <int KB, int THREADS, int NLD, bool USE_MATCH>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) hist_kernel(HistArgs a) {
+  using KT = KeyTile<KB, THREADS, NLD>;
+  const uint32_t f = a.plan->first_exec_p1;
+  if (f == 0) return;  // nothing will be swept
+  const int shift = (int)(f - 1) * RADIX_BITS;
+  const bool skewed = a.plan->skewed[f - 1] != 0;
+  __shared__ uint32_t sh[RADIX];
+  for (int i = threadIdx.x; i < RADIX; i += THREADS) sh[i] = 0;
+  __syncthreads();
+  const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    KT kt;
+    kt.load(a.keys, a.stride, a.n, tile, a.ko);
+    if (skewed) {
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const bool v = (kt.valid >> i) & 1;
+        const unsigned vmask = __ballot_sync(0xffffffffu, v);
+        if (v) hist_add<USE_MATCH>(sh, (uint32_t)(kt.u[i] >> shift) & (RADIX - 1), vmask);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++)
+        if ((kt.valid >> i) & 1) atomicAdd(&sh[(uint32_t)(kt.u[i] >> shift) & (RADIX - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  uint64_t *out = a.ghist + (size_t)(f - 1) * RADIX;
+  for (int i = threadIdx.x; i < RADIX; i += THREADS) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&out[i]), (unsigned long long)c);
   }
 }
 
@@ -196,49 +304,42 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(HistArgs a) {
 // bachelors-thesis.tex:4156-4176).  One block of RADIX threads.
 // ------------------------------------------------------------------------------------------------
 struct ScanArgs {
-  const uint64_t *ghist;   // [n_passes][RADIX], indexed by digit position
-  uint64_t *bin_base;      // [n_passes][RADIX] out
+  const uint64_t *ghist;   // [n_passes][RADIX] SAMPLED histograms from probe_kernel, indexed by digit position
+  const ProbeOut *probe;
   Plan *plan;
   int64_t n;
-  int n_passes;            // passes 0..n_passes-1 in execution order
-  int digit_of_pass[MAX_PASSES];
+  int n_passes;            // = key bytes; pass p sweeps digit position p
   int allow_skip;
-  int hybrid;              // 1: choose cut_digit (MSB hybrid); passes must be digit positions 0..n_passes-1
+  int hybrid;              // 1: choose cut_digit (MSB hybrid)
   float margin_bits;       // hybrid: sweep top digits until their entropies sum to log2(n) + margin_bits
 };
 
-__global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
-  __shared__ uint64_t warp_sum[RADIX / 32];
+static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
   __shared__ float warp_ent[RADIX / 32];
+  __shared__ unsigned long long warp_tot[RADIX / 32];
   __shared__ uint32_t s_skip[MAX_PASSES];
   __shared__ float s_entropy[MAX_PASSES];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t < MAX_PASSES) s_skip[t] = 0;
+  const unsigned long long varying = a.probe->or_bits & a.probe->nand_bits;  // bits on which keys differ
+  if (t < MAX_PASSES) s_skip[t] = (a.allow_skip && t < a.n_passes && ((varying >> (t * RADIX_BITS)) & (RADIX - 1)) == 0) ? 1 : 0;
   __syncthreads();
-  const float log2n = log2f((float)a.n);
   for (int p = 0; p < a.n_passes; p++) {
-    const int dp = a.digit_of_pass[p];
-    const uint64_t c = a.ghist[dp * RADIX + t];
-    if (a.allow_skip && c == (uint64_t)a.n) s_skip[p] = 1;
-    uint64_t inc = c;
-    float e = c ? (float)c * log2f((float)c) : 0.f;  // for the digit's entropy: log2 n - sum(c log2 c)/n
+    // entropy of digit position p on the sample: log2 m - sum(c log2 c)/m
+    const unsigned long long c = a.ghist[p * RADIX + t];
+    float e = c ? (float)c * log2f((float)c) : 0.f;
+    unsigned long long m = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += v;
+    for (int o = 16; o > 0; o >>= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+      m += __shfl_xor_sync(0xffffffffu, m, o);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    if (lane == 31) warp_sum[w] = inc;
-    if (lane == 0) warp_ent[w] = e;
+    if (lane == 0) { warp_ent[w] = e; warp_tot[w] = m; }
     __syncthreads();
-    uint64_t off = 0;
-    for (int i = 0; i < w; i++) off += warp_sum[i];
-    a.bin_base[p * RADIX + t] = off + inc - c;
     if (t == 0) {
       float tot = 0.f;
-      for (int i = 0; i < RADIX / 32; i++) tot += warp_ent[i];
-      s_entropy[p] = fmaxf(log2n - tot / (float)a.n, 0.f);
+      unsigned long long mm = 0;
+      for (int i = 0; i < RADIX / 32; i++) { tot += warp_ent[i]; mm += warp_tot[i]; }
+      s_entropy[p] = mm ? fmaxf(log2f((float)mm) - tot / (float)mm, 0.f) : 0.f;
     }
     __syncthreads();
   }
@@ -251,7 +352,7 @@ __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
       // segfix_kernel finishes them in shared memory.  A cut that saves fewer than two sweeps is not
       // worth the finishing pass.
       float acc = 0.f;
-      const float need = log2n + a.margin_bits;
+      const float need = log2f((float)a.n) + a.margin_bits;
       for (int p = a.n_passes - 1; p >= 0; p--) {
         if (!s_skip[p]) acc += s_entropy[p];
         if (acc >= need) { cut = (uint32_t)p; break; }
@@ -262,10 +363,19 @@ __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
       for (uint32_t p = 0; p < cut; p++) s_skip[p] = 1;
     }
     uint32_t sel = 0, n_exec = 0;
+    int prev = -1;
+    a.plan->first_exec_p1 = 0;
     for (int p = 0; p < a.n_passes; p++) {
       a.plan->skip[p] = s_skip[p];
       a.plan->src_sel[p] = sel;
-      if (!s_skip[p]) { sel ^= 1; n_exec++; }
+      a.plan->next_exec_p1[p] = 0;
+      a.plan->skewed[p] = s_entropy[p] < 5.0f ? 1u : 0u;
+      if (!s_skip[p]) {
+        sel ^= 1;
+        n_exec++;
+        if (prev < 0) a.plan->first_exec_p1 = (uint32_t)p + 1; else a.plan->next_exec_p1[prev] = (uint32_t)p + 1;
+        prev = p;
+      }
     }
     a.plan->final_sel = sel;
     a.plan->n_exec = n_exec;
@@ -290,7 +400,8 @@ struct SweepArgs {
   KeyOrder ko;
   int pass;                // index into plan / bin_base / tile_counter
   int shift;               // bit offset of this pass's digit in the ordered key
-  const uint64_t *bin_base;  // [RADIX] for this pass
+  const uint64_t *bin_base;  // [RADIX] bucket offsets of this pass, or nullptr: tile 0 scans ghist[pass]
+  uint64_t *ghist;           // [KB][RADIX] exact digit histograms (this pass reads its own, counts the next)
   uint64_t *lookback;      // [n_tiles][RADIX]
   uint32_t *tile_counter;  // one per pass
   const Plan *plan;
@@ -413,6 +524,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   uint32_t *s_wsum = s_prefix + RADIX;                                                        // 32
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
   uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
+  uint32_t *nhist = reinterpret_cast<uint32_t *>(sdigit + TILE);                             // RADIX (zeroed by the kernel)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile_base = tile * TILE;
@@ -439,6 +551,23 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   // ---- rank inside the warp (stable) -----------------------------------------------------------------
   uint32_t rank[IPT];
   uint32_t *wc = warp_cnt + warp * RADIX;
+  // the pass executed after this one gets its exact digit histogram from here (keys are in registers)
+  const uint32_t next_p1 = LUT ? 0u : a.plan->next_exec_p1[a.pass];
+  if (next_p1 != 0) {
+    const DigitX dn = make_digitx(a.ko, (int)(next_p1 - 1) * RADIX_BITS);
+    if (a.plan->skewed[next_p1 - 1]) {
+#pragma unroll
+      for (int r = 0; r < IPT; r++) {
+        const bool valid = FULL || idx0 + r * 32 < n_valid;
+        const unsigned vmask = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+        if (valid) hist_add<false>(nhist, fast_digit<KB>(raw[r], dn), vmask);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < IPT; r++)
+        if (FULL || idx0 + r * 32 < n_valid) atomicAdd(&nhist[fast_digit<KB>(raw[r], dn)], 1u);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
     const uint32_t d = digit_of(r);
@@ -455,6 +584,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   // ---- per-digit totals: exclusive scan across warps, then across digits ----------------------------
   uint32_t my_count = 0;
   if (tid < RADIX) {
+    if (next_p1 != 0) {
+      const uint32_t c = nhist[tid];
+      if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ghist[(size_t)(next_p1 - 1) * RADIX + tid]), (unsigned long long)c);
+    }
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < NWARPS; w++) {
@@ -472,7 +605,28 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     if (lane == 31) s_wsum[warp] = inc;
     s_prefix[tid] = inc - run;  // exclusive within the warp's 32 digits; warp offset added below
   }
+  // tile 0 turns the pass's exact histogram into bucket offsets (exclusive scan over the 256 counts)
+  uint64_t tile0_base = 0, t0_inc = 0, t0_cnt = 0;
+  if (tile == 0 && tid < RADIX) {
+    if (a.bin_base != nullptr) {
+      tile0_base = a.bin_base[tid];
+    } else {
+      t0_cnt = a.ghist[(size_t)a.pass * RADIX + tid];
+      t0_inc = t0_cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t v = __shfl_up_sync(0xffffffffu, t0_inc, o);
+        if (lane >= o) t0_inc += v;
+      }
+      if (lane == 31) gbase[warp] = (int64_t)t0_inc;  // gbase is free until the look-back
+    }
+  }
   __syncthreads();
+  if (tile == 0 && tid < RADIX && a.bin_base == nullptr) {
+    uint64_t off = 0;
+    for (int w = 0; w < warp; w++) off += (uint64_t)gbase[w];
+    tile0_base = off + t0_inc - t0_cnt;
+  }
   const uint64_t tagbits = (uint64_t)a.tag << LB_TAG_SHIFT;
   uint64_t valid_count = 0;
   if (tid < RADIX) {
@@ -483,7 +637,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     valid_count = my_count - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
     uint64_t *slot = &a.lookback[(size_t)tile * RADIX + tid];
     if (tile == 0)
-      st_relaxed_u64(slot, LB_FLAG_PREFIX | tagbits | (a.bin_base[tid] + valid_count));
+      st_relaxed_u64(slot, LB_FLAG_PREFIX | tagbits | (tile0_base + valid_count));
     else
       st_relaxed_u64(slot, LB_FLAG_AGG | tagbits | valid_count);
   }
@@ -538,7 +692,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   if (tid < RADIX) {
     uint64_t excl;
     if (tile == 0) {
-      excl = a.bin_base[tid];
+      excl = tile0_base;
     } else {
       constexpr int LB_BATCH = 4;
       excl = 0;
@@ -621,6 +775,10 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
   for (int i = threadIdx.x; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
+  {
+    uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + NWARPS * RADIX) + RADIX * 8 + RADIX * 4 + 32 * 4 + TILE * 3);
+    for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
+  }
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
@@ -639,7 +797,7 @@ struct CopyBackArgs {
   const Plan *plan;
 };
 
-__global__ void __launch_bounds__(256) copyback_kernel(const __grid_constant__ CopyBackArgs a) {
+static __global__ void __launch_bounds__(256) copyback_kernel(const __grid_constant__ CopyBackArgs a) {
   if (a.plan->final_sel == 0 || a.plan->cut_digit != 0) return;  // (the segment finish already wrote side 0)
   for (int s = 0; s < a.ss.n_streams; s++) {
     const Stream &st = a.ss.streams[s];

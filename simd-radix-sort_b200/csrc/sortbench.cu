@@ -103,7 +103,7 @@ int main(int argc, char **argv) {
   int64_t n = 1 << 24;
   std::string key = "u64";
   std::vector<int> pay;
-  int iters = 3, dist = 0, asc = 1, aos = 0, verify = 1;
+  int iters = 3, dist = 0, asc = 1, aos = 0, verify = 1, prof = 0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() { return std::string(argv[++i]); };
@@ -115,6 +115,7 @@ int main(int argc, char **argv) {
     else if (a == "--desc") asc = 0;
     else if (a == "--aos") aos = atoi(next().c_str());   // record bytes
     else if (a == "--noverify") verify = 0;
+    else if (a == "--prof") { prof = 1; b200sort_set_option("profile", 1); }
     else if (a == "--opt") { std::string s = next(); size_t e = s.find('='); if (b200sort_set_option(s.substr(0, e).c_str(), atoll(s.substr(e + 1).c_str()))) { fprintf(stderr, "%s\n", b200sort_last_error()); return 2; } }
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -174,6 +175,14 @@ int main(int argc, char **argv) {
       CK(cudaMemcpy(err, d_err, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&sum1, d_sum, 8, cudaMemcpyDeviceToHost));
       if (err[0] || err[1] || sum1 != sum0) { printf("VERIFY FAILED: order_violations=%llu payload_mismatch=%llu checksum %s\n", err[0], err[1], sum1 == sum0 ? "ok" : "DIFFERS"); rc_all = 1; }
     }
+  }
+  if (prof) {
+    int kinds[64]; float ms[64];
+    const int np = b200sort_last_profile(kinds, ms, 64);
+    static const char *names[] = {"hist", "scan", "sweep", "copyback", "segfix", "other"};
+    printf("  per-kernel ms:");
+    for (int i = 0; i < np; i++) printf(" %s=%.3f", names[kinds[i] < 6 ? kinds[i] : 5], ms[i]);
+    printf("\n");
   }
   b200sort_stats st{};
   b200sort_last_stats(&st);
