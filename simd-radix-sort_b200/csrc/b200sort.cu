@@ -115,8 +115,7 @@ static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstag
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
 
-static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int mode, cudaStream_t st) {
-  (void)mode;
+static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int sm_count, cudaStream_t st) {
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   int n_cols = 0;
   const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == (uint32_t)kb;
@@ -144,6 +143,7 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
+  (void)sm_count;
   k<<<(unsigned)n_tiles, tc.threads, smem, st>>>(a);
   g_launches++;
   return cudaGetLastError();
@@ -366,22 +366,37 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 
+    // Large hybrid sorts read the plan back (small D2H; the host waits on an event recorded right after
+    // it, while the histogram kernel below already runs) and launch only the passes that execute;
+    // otherwise every pass is launched and the skipped ones return at once.
+    Plan hplan{};
+    bool have_plan = false;
+    static thread_local cudaEvent_t plan_event = nullptr;
+    if (hybrid && n >= (int64_t)1 << 24) {
+      if (plan_event == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&plan_event, cudaEventDisableTiming));
+      CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaEventRecord(plan_event, stream));
+      have_plan = true;
+    }
+
     // exact histogram of the first executed pass only; every pass counts its successor's digit
     HistArgs hb = ha;
     hb.ghist = ghist_exact; hb.plan = plan; hb.probe = nullptr;
     CUDA_TRY(launch_hist(kb, hb, di.sm_count, /*probe=*/false, stream));
 
+    if (have_plan) CUDA_TRY(cudaEventSynchronize(plan_event));
     const int64_t n_tiles = (n + tile - 1) / tile;
     for (int p = 0; p < kb; p++) {
+      if (have_plan && hplan.skip[p]) continue;
       SweepArgs wa{};
       wa.ss = ss; wa.n = n; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
       wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
-      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, 0, stream));
+      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream));
     }
     HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
-    if (hybrid) {
+    if (hybrid && !(have_plan && hplan.cut_digit == 0)) {
       SegfixArgs fa{};
       fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl;
       bool any = false;
@@ -409,9 +424,8 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     if (hybrid) {
       // The plan was made on the device; read it (and the fall-back flag) back.  This is the one host
       // synchronisation of the hybrid path.
-      Plan hplan{};
       HybridCtrl hctrl{};
-      CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
+      if (!have_plan) CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaMemcpyAsync(&hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
       stt.passes_planned = hplan.n_exec;

@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
 #pragma unroll
     for (int i = 0; i < KT::PER_THREAD; i++)
       if ((kt.valid >> i) & 1) { acc_or |= kt.u[i]; acc_nand |= ~kt.u[i]; }
-    if (tile % a.sample == 0) {
+    // every CTA samples every sample-th of ITS OWN tiles (tile % sample would pile all sampled tiles on
+    // 1/sample of the CTAs when the grid size is a multiple of sample)
+    if (((tile / gridDim.x) + blockIdx.x) % a.sample == 0) {
 #pragma unroll
       for (int i = 0; i < KT::PER_THREAD; i++) {
         const bool v = (kt.valid >> i) & 1;
@@ -772,13 +774,15 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
 
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * TILE * a.stage_bytes);
+  uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + NWARPS * RADIX) + RADIX * 8 +
+                                                 RADIX * 4 + 32 * 4 + TILE * 3);
+  // One tile per CTA.  (A persistent grid that loops over tickets was measured 17 % slower: CTAs that
+  // start together stay in phase, so loads, look-backs and stores of the whole machine bunch up; fresh
+  // CTAs per tile stagger naturally.  profiles/README.md)
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
   for (int i = threadIdx.x; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
-  {
-    uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + NWARPS * RADIX) + RADIX * 8 + RADIX * 4 + 32 * 4 + TILE * 3);
-    for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
-  }
+  for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;

@@ -294,7 +294,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
     wa.bin_base = c->d_bin_base; wa.lookback = (uint64_t *)(ws + L.lookback_off);
     wa.tile_counter = (uint32_t *)(ws + L.tilectr_off); wa.plan = c->d_plan; wa.tag = 1; wa.stage_bytes = stage_bytes;
     wa.lut = c->d_lut; wa.lut_shift = shift;
-    CUDA_TRY(launch_sweep(kb, cfg, wa, (num_local + tile - 1) / tile, di.smem_optin, 0, stream));
+    CUDA_TRY(launch_sweep(kb, cfg, wa, (num_local + tile - 1) / tile, di.smem_optin, di.sm_count, stream));
     // bin_base / plan / lut live in the communicator and are reused: the copies above are stream-ordered,
     // but the host arrays are stack/vector memory, so wait before they go out of scope
     CUDA_TRY(cudaStreamSynchronize(stream));
