@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_RECORDS, help="records per GPU (development override)")
+    ap.add_argument("--records", dest="n", type=int, default=N_RECORDS, help="records per GPU (development override)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=1 << 27)
     return ap.parse_args()
@@ -107,7 +107,7 @@ def run_reference_arm(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -123,7 +123,7 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -134,12 +134,17 @@ class ClockSampler:
         self.tmp.flush()
         rows = [r.strip().split(", ") for r in Path(self.tmp.name).read_text().splitlines() if r.strip()]
         os.unlink(self.tmp.name)
+        import datetime
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                if t_begin is not None:
+                    ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t_begin - 0.05 or ts > t_end + 0.05:
+                        continue
+                sm.append(float(r[2])); mx.append(float(r[3]))
                 names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for name, val in zip(names, r[5:9]):
+                for name, val in zip(names, r[6:10]):
                     if val.strip().lower() == "active":
                         reasons.add(name)
             except Exception:
@@ -245,6 +250,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a moment to start; only samples inside the timed region are kept
     # ---- warm-up (also the correctness gate: a fast wrong sort is not a result) ----
     for w in range(args.warmup):
         restore()
@@ -274,13 +282,11 @@ def main():
 
     # ---- timed steps ----
     S.set_option("profile", 1)
-    sampler = ClockSampler(local_rank)
     step_ms = []
     prof = []
     launches0 = S.launch_count()
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_begin = time.time()
     for k in range(args.steps):
         restore()
         if multi:
@@ -293,7 +299,8 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
         prof.append(S.last_profile())
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = S.launch_count() - launches0
     S.set_option("profile", 0)
     stats = S.last_stats()
@@ -367,6 +374,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "onesweep_kernel (digit scatter pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "peak_source": peak_src,
                 "traffic": traffic * (n_sweep_launch / 67108864) if traffic else None,
+                "traffic_source": "profiles/dominant_kernel_traffic.json (ncu --set full at 2^26 records, scaled linearly)" if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_sweep,
                 "sweep_launches_per_step": len(sweep_ms) / args.steps,
                 "ms_per_step_by_kernel": per_kind,

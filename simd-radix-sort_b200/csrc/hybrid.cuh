@@ -15,7 +15,7 @@
 namespace b200sort {
 
 constexpr int SF_THREADS = 256;
-constexpr int SF_FT = 2048;                      // positions a tile is responsible for
+constexpr int SF_FT = 4096;                      // positions a tile is responsible for
 constexpr int SF_HALO = 256;                     // keys read on either side to see whole segments
 constexpr int SF_MAXSEG = SF_HALO;               // longest segment ordered in shared memory
 constexpr int SF_W = SF_FT + 2 * SF_HALO;        // window
@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
 
   __shared__ O wkey[SF_W];
   __shared__ uint32_t hbits[SF_W / 32 + 2];  // one bit per window position: set = first key of a segment
+  __shared__ uint16_t q_p[SF_W];              // move queue: window position ...
+  __shared__ uint16_t q_d[SF_W];              // ... and where it goes
+  __shared__ int q_n;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t s0 = (int64_t)blockIdx.x * SF_FT;
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
     if (p < wn) wkey[p] = to_ordered<KB>(load_key<KB>(ksrc, w0 + p, key_stride), a.ko);
   }
   if (tid < 2) hbits[SF_W / 32 + tid] = 0;
+  if (tid == 0) q_n = 0;
   __syncthreads();
 
   // a position is a segment head when its prefix differs from its left neighbour's
@@ -120,11 +124,6 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
   };
 
   // ---- classify every window position; rank inside short segments; queue what has to move --------------
-  __shared__ uint16_t q_p[SF_W];
-  __shared__ uint16_t q_d[SF_W];
-  __shared__ int q_n;
-  if (tid == 0) q_n = 0;
-  __syncthreads();
   const int off_s = (int)(s0 - w0), off_e = (int)(e0 - w0);  // this tile's own positions inside the window
   bool fail = false;
 #pragma unroll 2

@@ -718,6 +718,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           }
         }
         t -= consumed;
+        if (consumed == 0) __nanosleep(40);  // nothing published yet: do not burn issue slots the other CTAs need
       }
       st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
     }
