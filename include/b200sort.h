@@ -119,6 +119,7 @@ typedef struct b200sort_stats {
   uint32_t cut_digit;         /* hybrid: digit positions below this were left to the segment finish */
   uint32_t fell_back;         /* hybrid: 1 when a long bucket with distinct keys forced the digit-by-digit path */
   uint64_t algorithmic_bytes; /* H*N*K + P*2*N*R with the executed pass counts */
+  uint64_t segfix_moved;      /* hybrid: records the segment finish had to move */
 } b200sort_stats;
 int b200sort_last_stats(b200sort_stats *out);
 

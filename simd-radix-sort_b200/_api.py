@@ -24,7 +24,7 @@ class _Stats(ctypes.Structure):
     _fields_ = [("num", ctypes.c_int64), ("record_bytes", ctypes.c_uint32), ("key_bytes", ctypes.c_uint32),
                 ("algo", ctypes.c_uint32), ("passes_planned", ctypes.c_uint32), ("hist_sweeps", ctypes.c_uint32),
                 ("kernel_launches", ctypes.c_uint32), ("segfix_passes", ctypes.c_uint32), ("cut_digit", ctypes.c_uint32),
-                ("fell_back", ctypes.c_uint32), ("algorithmic_bytes", ctypes.c_uint64)]
+                ("fell_back", ctypes.c_uint32), ("algorithmic_bytes", ctypes.c_uint64), ("segfix_moved", ctypes.c_uint64)]
 
 
 _lib = None

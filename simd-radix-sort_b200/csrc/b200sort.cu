@@ -36,6 +36,8 @@ static std::atomic<int64_t> opt_algo{0};       // 0 auto, 1 LSD, 2 hybrid
 static std::atomic<int64_t> opt_tile_cfg{-1};  // -1 auto
 static std::atomic<int64_t> opt_use_match{0};
 static std::atomic<int64_t> opt_allow_skip{1};
+static std::atomic<int64_t> opt_allow_reduce{1};
+static std::atomic<int64_t> opt_spin_ns{0};
 static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 
@@ -96,7 +98,7 @@ KeyOrder make_key_order(int key_type, bool ascending) {
   const bool is_signed = key_type == B200SORT_I8 || key_type == B200SORT_I16 || key_type == B200SORT_I32 ||
                          key_type == B200SORT_I64;
   const bool is_float = key_type == B200SORT_F32 || key_type == B200SORT_F64;
-  KeyOrder ko{0, 0};
+  KeyOrder ko{0, 0, 0};
   if (is_signed || is_float) ko.xor_const = sign;
   if (is_float) ko.neg_xor = mask ^ sign;
   if (!ascending) ko.xor_const ^= mask;
@@ -358,6 +360,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     sa.ghist = ghist; sa.probe = probe; sa.plan = plan; sa.n = n; sa.n_passes = kb;
     sa.allow_skip = (int)opt_allow_skip.load();
     sa.hybrid = hybrid ? 1 : 0;
+    sa.allow_reduce = (int)opt_allow_reduce.load();
     sa.margin_bits = (float)opt_margin_bits.load();
     {
       ProfScope ps(PK_SCAN, stream);
@@ -392,13 +395,18 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       wa.ss = ss; wa.n = n; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
       wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
-      wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes;
+      wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes; wa.spin_ns = (uint32_t)opt_spin_ns.load();
+      if (have_plan) {
+        wa.plan_in_args = 1; wa.arg_sel = hplan.src_sel[p]; wa.arg_next_p1 = hplan.next_exec_p1[p];
+        wa.arg_next_skewed = hplan.next_exec_p1[p] ? hplan.skewed[hplan.next_exec_p1[p] - 1] : 0; wa.arg_sub = hplan.sub;
+      }
       CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream));
     }
     HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
     if (hybrid && !(have_plan && hplan.cut_digit == 0)) {
       SegfixArgs fa{};
       fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl;
+      if (have_plan) { fa.plan_in_args = 1; fa.arg_cut = hplan.cut_digit; fa.arg_sel = hplan.final_sel; fa.arg_sub = hplan.sub; }
       bool any = false;
       for (int s = 0; s < ss.n_streams; s++) any = any || ss.streams[s].chunk_bytes < 4;
       const unsigned grid = (unsigned)((n + SF_FT - 1) / SF_FT);
@@ -431,6 +439,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       stt.passes_planned = hplan.n_exec;
       stt.segfix_passes = hplan.cut_digit != 0 ? 1 : 0;
       stt.cut_digit = hplan.cut_digit;
+      memcpy(&stt.segfix_moved, &hctrl.flags[2], 8);
       stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
       if (hctrl.flags[0] != 0) {
         // a long bucket with distinct keys: finish with the plain digit-by-digit path (the array is a
@@ -617,6 +626,8 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "tile_cfg")) return &opt_tile_cfg;
   if (!strcmp(name, "use_match")) return &opt_use_match;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
+  if (!strcmp(name, "allow_reduce")) return &opt_allow_reduce;
+  if (!strcmp(name, "spin_ns")) return &opt_spin_ns;
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;

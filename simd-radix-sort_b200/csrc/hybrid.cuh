@@ -14,20 +14,23 @@
 
 namespace b200sort {
 
-constexpr int SF_THREADS = 256;
-constexpr int SF_FT = 4096;                      // positions a tile is responsible for
-constexpr int SF_HALO = 256;                     // keys read on either side to see whole segments
+constexpr int SF_THREADS = 256;                  // 8 warps, each finishing its own chunk: no block barriers
+constexpr int SF_WARPS = SF_THREADS / 32;
+constexpr int SF_CHUNK = 256;                    // positions a warp is responsible for
+constexpr int SF_HALO = 32;                      // keys read on either side to see whole segments
 constexpr int SF_MAXSEG = SF_HALO;               // longest segment ordered in shared memory
-constexpr int SF_W = SF_FT + 2 * SF_HALO;        // window
-constexpr int SF_PPT = SF_W / SF_THREADS;        // window positions per thread
-constexpr int SF_BIG = 32767;
-static_assert(SF_W % SF_THREADS == 0 && SF_W < SF_BIG, "window geometry");
+constexpr int SF_W = SF_CHUNK + 2 * SF_HALO;     // window of a warp
+constexpr int SF_PPT = SF_W / 32;                // window positions per lane
+constexpr int SF_FT = SF_CHUNK * SF_WARPS;       // positions per CTA
+constexpr int SF_BIG = 1 << 20;
+static_assert(SF_W % 32 == 0, "window geometry");
 
 constexpr int HYB_MIN_TILE = 2048;               // smallest tile any kernel uses (sizes the look-back array)
 constexpr int64_t HYB_MIN_N = 1 << 22;           // below this the plain digit-by-digit path is used
 
 struct HybridCtrl {
-  uint32_t flags[64];   // [0] != 0: a long segment with distinct keys was met -> host falls back
+  uint32_t flags[64];   // [0] != 0: a long segment with distinct keys was met -> host falls back;
+                        // [2..3]: 64-bit count of records the finish moved (statistics)
 };
 
 struct SegfixArgs {
@@ -36,119 +39,122 @@ struct SegfixArgs {
   KeyOrder ko;
   const Plan *plan;
   HybridCtrl *ctrl;
+  // plan values as arguments when the host has read the plan back (no dependent load at CTA start)
+  uint32_t plan_in_args, arg_cut, arg_sel;
+  unsigned long long arg_sub;
 };
 
-// Moves the queued elements of one chunk column: entry i goes from window position q_p[i] to q_d[i].
-// Source and destination may be the same array, so everything is read before anything is written.
-// Moves the queued elements of one chunk column: entry i goes from window position q_p[i] to q_d[i].
-// Source and destination may be the same array, so the whole column is read into shared memory (the
-// key window is no longer needed and is reused as the buffer) before anything is written.
+// Moves the queued elements of one chunk column (one warp): entry i goes from window position q_p[i] to
+// q_d[i].  Source and destination may be the same array, so the whole column is read into the warp's
+// shared-memory scratch (the key window, no longer needed) before anything is written.
 template <typename T>
 __device__ __forceinline__ void segfix_move(const unsigned char *src, unsigned char *dst, int64_t w0, const uint16_t *q_p,
-                                            const uint16_t *q_d, int count, uint32_t cpe, uint32_t c, void *stage_raw) {
+                                            const uint16_t *q_d, int count, uint32_t cpe, uint32_t c, void *stage_raw, int lane) {
   static_assert(sizeof(T) <= 8, "columns wider than 8 bytes are moved as 8-byte halves");
   const T *s = reinterpret_cast<const T *>(src) + (size_t)w0 * cpe + c;
   T *d = reinterpret_cast<T *>(dst) + (size_t)w0 * cpe + c;
   T *stage = reinterpret_cast<T *>(stage_raw);
-  for (int i = threadIdx.x; i < count; i += SF_THREADS) stage[i] = s[(size_t)q_p[i] * cpe];
-  __syncthreads();
-  for (int i = threadIdx.x; i < count; i += SF_THREADS) d[(size_t)q_d[i] * cpe] = stage[i];
-  __syncthreads();
+  for (int i = lane; i < count; i += 32) stage[i] = s[(size_t)q_p[i] * cpe];
+  __syncwarp();
+  for (int i = lane; i < count; i += 32) d[(size_t)q_d[i] * cpe] = stage[i];
+  __syncwarp();
 }
 
+// One warp per chunk of SF_CHUNK positions, everything warp-synchronous:
+//  1. the warp loads its window (chunk + SF_HALO keys on either side) as ordered keys;
+//  2. a position is a segment head when its prefix (bits >= 8*cut) differs from its left neighbour's;
+//     the head flags of the window are ten ballot words that every lane holds in registers;
+//  3. one-key segments (the common case) need nothing; a short segment (<= SF_MAXSEG keys, hence fully
+//     inside the window of every warp it touches) is ordered by rank counting by the warp that owns its
+//     head; a long segment must consist of one repeated key (duplicates) -- a long segment with distinct
+//     keys raises ctrl->flags[0];
+//  4. the records that have to move (all owned ones when the data still sits in the shadow, only the
+//     displaced ones when it already lies in the caller's arrays) are queued and moved column by column.
 template <int KB, bool ANYCHUNK>
 __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_constant__ SegfixArgs a) {
   using O = typename OrdOf<KB>::type;
-  const uint32_t cut = a.plan->cut_digit;
+  const uint32_t cut = a.plan_in_args ? a.arg_cut : a.plan->cut_digit;
   if (cut == 0) return;  // every varying digit was swept: nothing to finish
-  const uint32_t sel = a.plan->final_sel;
+  const uint32_t sel = a.plan_in_args ? a.arg_sel : a.plan->final_sel;
 
-  __shared__ O wkey[SF_W];
-  __shared__ uint32_t hbits[SF_W / 32 + 2];  // one bit per window position: set = first key of a segment
-  __shared__ uint16_t q_p[SF_W];              // move queue: window position ...
-  __shared__ uint16_t q_d[SF_W];              // ... and where it goes
-  __shared__ int q_n;
+  __shared__ O s_wkey[SF_WARPS][SF_W];
+  __shared__ uint16_t s_qp[SF_WARPS][SF_W];
+  __shared__ uint16_t s_qd[SF_WARPS][SF_W];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t s0 = (int64_t)blockIdx.x * SF_FT;
-  const int64_t e0 = s0 + SF_FT < a.n ? s0 + SF_FT : a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  O *wkey = s_wkey[warp];
+  uint16_t *q_p = s_qp[warp], *q_d = s_qd[warp];
+  const int64_t s0 = ((int64_t)blockIdx.x * SF_WARPS + warp) * SF_CHUNK;
+  if (s0 >= a.n) return;
+  const int64_t e0 = s0 + SF_CHUNK < a.n ? s0 + SF_CHUNK : a.n;
   const int64_t w0 = s0 - SF_HALO > 0 ? s0 - SF_HALO : 0;
   const int64_t w1 = e0 + SF_HALO < a.n ? e0 + SF_HALO : a.n;
   const int wn = (int)(w1 - w0);
+  const int off_s = (int)(s0 - w0), off_e = (int)(e0 - w0);  // the chunk's own positions inside the window
   const O pmask = (O)(~(O)0) << (8 * cut);  // cut < KB
 
   const Stream &ks = a.ss.streams[0];
   const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
   const unsigned char *ksrc = ks.buf[sel];
+  KeyOrder ko = a.ko;
+  ko.sub = a.plan_in_args ? a.arg_sub : a.plan->sub;
+
+  O key[SF_PPT];
 #pragma unroll
-  for (int k = 0; k < SF_PPT; k++) {
-    const int p = tid + k * SF_THREADS;
-    if (p < wn) wkey[p] = to_ordered<KB>(load_key<KB>(ksrc, w0 + p, key_stride), a.ko);
+  for (int j = 0; j < SF_PPT; j++) {
+    const int p = j * 32 + lane;
+    key[j] = p < wn ? to_ordered<KB>(load_key<KB>(ksrc, w0 + p, key_stride), ko) : (O)0;
   }
-  if (tid < 2) hbits[SF_W / 32 + tid] = 0;
-  if (tid == 0) q_n = 0;
-  __syncthreads();
-
-  // a position is a segment head when its prefix differs from its left neighbour's
-  auto is_head = [&](int p) -> bool {
-    if (p == 0) return w0 == 0;  // unknown when the window does not start at the array start
-    return ((wkey[p] ^ wkey[p - 1]) & pmask) != 0;
-  };
-  // head bits, one 32-bit word per warp and step; the array end closes the last segment
 #pragma unroll
-  for (int k = 0; k < SF_PPT; k++) {
-    const int p = tid + k * SF_THREADS;
-    const bool h = (p < wn && is_head(p)) || (p == wn && w1 == a.n);
-    const unsigned word = __ballot_sync(0xffffffffu, h);
-    if (lane == 0) hbits[warp + k * (SF_THREADS / 32)] = word;
+  for (int j = 0; j < SF_PPT; j++) wkey[j * 32 + lane] = key[j];
+  __syncwarp();
+
+  // head flags: hb[j] bit l <-> window position 32 j + l; the array end closes the last segment
+  uint32_t hb[SF_PPT + 2];
+#pragma unroll
+  for (int j = 0; j < SF_PPT; j++) {
+    const int p = j * 32 + lane;
+    bool h = false;
+    if (p < wn) h = p == 0 ? (w0 == 0) : (((key[j] ^ wkey[p - 1]) & pmask) != 0);  // p == 0: unknown unless the array starts here
+    else if (p == wn) h = w1 == a.n;
+    hb[j] = __ballot_sync(0xffffffffu, h);
   }
-  if (tid == 0 && wn == SF_W && w1 == a.n) hbits[SF_W / 32] = 1u;
-  __syncthreads();
+  hb[SF_PPT] = (wn == SF_W && w1 == a.n) ? 1u : 0u;
+  hb[SF_PPT + 1] = 0u;
 
-  constexpr int MAXWORDS = SF_MAXSEG / 32;
-  // start of the segment holding p: the nearest head at or before p (-1: none within SF_MAXSEG)
-  auto seg_start = [&](int p) -> int {
-    int w = p >> 5;
-    uint32_t m = hbits[w] & (0xffffffffu >> (31 - (p & 31)));
-    if (m == 0)
-      for (int s = 0; m == 0 && w > 0 && s < MAXWORDS; s++) m = hbits[--w];
-    return m ? (w << 5) + 31 - __clz(m) : -1;
-  };
-  // end of the segment holding p: the nearest head after p (SF_BIG: none within SF_MAXSEG)
-  auto seg_end = [&](int p) -> int {
-    int w = p >> 5;
-    uint32_t m = hbits[w] & ~(0xffffffffu >> (31 - (p & 31)));  // bits above p
-    if (m == 0)
-      for (int s = 0; m == 0 && w < SF_W / 32 && s < MAXWORDS; s++) m = hbits[++w];
-    return m ? (w << 5) + __ffs(m) - 1 : SF_BIG;
-  };
-
-  // ---- classify every window position; rank inside short segments; queue what has to move --------------
-  const int off_s = (int)(s0 - w0), off_e = (int)(e0 - w0);  // this tile's own positions inside the window
+  int q_count = 0;  // uniform across the warp
   bool fail = false;
-#pragma unroll 2
-  for (int k = 0; k < SF_PPT; k++) {
-    const int p = tid + k * SF_THREADS;
+#pragma unroll
+  for (int j = 0; j < SF_PPT; j++) {
+    const int p = j * 32 + lane;
     int dest = p;
     bool act = false;
-    // a head directly followed by another head is a one-key bucket: nothing to order (the common case);
-    // in place it does not even have to move
-    const uint32_t two = (uint32_t)((((uint64_t)hbits[(p >> 5) + 1] << 32) | hbits[p >> 5]) >> (p & 31)) & 3u;
+    const uint32_t cur = hb[j], nxt = hb[j + 1], prv = j > 0 ? hb[j - 1] : 0u;
+    const uint32_t two = __funnelshift_r(cur, nxt, lane) & 3u;  // head bits of p and p + 1
     if (p < wn && two == 3u) {
+      // a head directly followed by a head: one-key segment, nothing to order
       act = sel != 0 && p >= off_s && p < off_e;
     } else if (p < wn) {
-      const int st = seg_start(p), en = seg_end(p);
+      // start: nearest head at or before p (this word, else the previous one = up to 63 positions back)
+      int st = -1;
+      const uint32_t below = cur & (0xffffffffu >> (31 - lane));
+      if (below) st = j * 32 + 31 - __clz(below);
+      else if (prv) st = (j - 1) * 32 + 31 - __clz(prv);
+      // end: nearest head after p (this word, else the next one)
+      int en = SF_BIG;
+      const uint32_t above = cur & ~(0xffffffffu >> (31 - lane));
+      if (above) en = j * 32 + __ffs(above) - 1;
+      else if (nxt) en = (j + 1) * 32 + __ffs(nxt) - 1;
       const bool is_long = st < 0 || en == SF_BIG || (en - st) > SF_MAXSEG;
       if (is_long) {
-        // long segments stay as they are (and must consist of one repeated key); the tile that owns the
-        // position copies it when the data still sits in the shadow
+        // long segments stay as they are and must consist of one repeated key
         if (p >= off_s && p < off_e) {
           act = sel != 0;
-          if (p > 0 && !is_head(p) && wkey[p] != wkey[p - 1]) fail = true;
+          if (p > 0 && ((cur >> lane) & 1u) == 0 && key[j] != wkey[p - 1]) fail = true;
         }
-      } else if (st >= off_s && st < off_e) {  // the tile holding a segment's head orders the whole segment
+      } else if (st >= off_s && st < off_e) {  // the chunk holding a segment's head orders the whole segment
         if (en - st > 1) {
-          const O mine = wkey[p];
+          const O mine = key[j];
           int cnt = 0;
           for (int q = st; q < en; q++) {
             const O o = wkey[q];
@@ -156,25 +162,23 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
           }
           dest = st + cnt;
         }
-        act = sel != 0 || dest != p;  // in place only displaced elements move
+        // In place only displaced records move.  (Writing whole aligned 4-record groups instead of single
+        // records was measured slower, 13.1 vs 11.5 ms at 1e9: profiles/README.md.)
+        act = sel != 0 || dest != p;
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, act);
-    if (m) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&q_n, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (act) {
-        const int i = base + __popc(m & lanemask_lt());
-        q_p[i] = (uint16_t)p;
-        q_d[i] = (uint16_t)dest;
-      }
+    if (act) {
+      const int i = q_count + __popc(m & lanemask_lt());
+      q_p[i] = (uint16_t)p;
+      q_d[i] = (uint16_t)dest;
     }
+    q_count += __popc(m);
   }
   if (__any_sync(0xffffffffu, fail) && lane == 0) atomicOr(&a.ctrl->flags[0], 1u);
-  __syncthreads();
-  const int count = q_n;
-  if (count == 0) return;
+  __syncwarp();
+  if (q_count == 0) return;
+  if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ctrl->flags[2]), (unsigned long long)q_count);  // statistics
 
   // ---- move every stream: window position q_p -> q_d (side `sel` -> side 0) -------------------------------
   for (int s = 0; s < a.ss.n_streams; s++) {
@@ -183,14 +187,14 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
     unsigned char *dst = st.buf[0];
     for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
       const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
-      if (cb == 8) segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
-      else if (cb == 4) segfix_move<uint32_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
+      if (cb == 8) segfix_move<uint64_t>(src, dst, w0, q_p, q_d, q_count, cpe, c, wkey, lane);
+      else if (cb == 4) segfix_move<uint32_t>(src, dst, w0, q_p, q_d, q_count, cpe, c, wkey, lane);
       else if (cb == 16) {
-        segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, cpe * 2, c * 2, wkey);
-        segfix_move<uint64_t>(src, dst, w0, q_p, q_d, count, cpe * 2, c * 2 + 1, wkey);
+        segfix_move<uint64_t>(src, dst, w0, q_p, q_d, q_count, cpe * 2, c * 2, wkey, lane);
+        segfix_move<uint64_t>(src, dst, w0, q_p, q_d, q_count, cpe * 2, c * 2 + 1, wkey, lane);
       } else if constexpr (ANYCHUNK) {
-        if (cb == 2) segfix_move<uint16_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
-        else segfix_move<uint8_t>(src, dst, w0, q_p, q_d, count, cpe, c, wkey);
+        if (cb == 2) segfix_move<uint16_t>(src, dst, w0, q_p, q_d, q_count, cpe, c, wkey, lane);
+        else segfix_move<uint8_t>(src, dst, w0, q_p, q_d, q_count, cpe, c, wkey, lane);
       }
     }
   }

@@ -37,6 +37,9 @@ template <> struct OrdOf<8> { using type = uint64_t; };
 struct KeyOrder {
   uint64_t xor_const;  // SIGN for signed/float, ^ MASK when descending
   uint64_t neg_xor;    // MASK ^ SIGN for float keys, else 0
+  uint64_t sub;        // range reduction: the smallest mapped key of this sort (or 0), subtracted last.
+                       // Keys of a narrow range that straddles the sign (e.g. -8..7, N(0,100)) differ in every
+                       // digit position; after the subtraction only the low digit positions vary.
 };
 
 template <int KB>
@@ -44,7 +47,7 @@ __device__ __forceinline__ typename OrdOf<KB>::type to_ordered(typename UIntOf<K
   using O = typename OrdOf<KB>::type;
   O u = (O)raw;
   const O neg = (O)0 - ((u >> (8 * KB - 1)) & 1);  // all ones when the sign bit is set
-  return u ^ (O)ko.xor_const ^ (neg & (O)ko.neg_xor);
+  return (u ^ (O)ko.xor_const ^ (neg & (O)ko.neg_xor)) - (O)ko.sub;
 }
 
 template <int KB>
@@ -84,12 +87,15 @@ struct Plan {
   uint32_t first_exec_p1;
   uint32_t next_exec_p1[MAX_PASSES];
   uint32_t skewed[MAX_PASSES];  // digit position has a low-entropy histogram: aggregate equal digits per warp
+  unsigned long long sub;       // range reduction (KeyOrder::sub) chosen by the plan, 0 = none
 };
 
 // per-sort scalars produced by probe_kernel (zero-initialised by the host)
 struct ProbeOut {
   unsigned long long or_bits;    // OR of all ordered keys
   unsigned long long nand_bits;  // OR of the complements: a bit varies iff it is set in both words
+  unsigned long long max_key;    // largest ordered key
+  unsigned long long nmin_key;   // complement of the smallest ordered key (so that zero-initialisation works)
 };
 
 // look-back status word: [63:62] flag, [61:57] generation tag, [56:0] value
@@ -224,13 +230,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
   for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) sh[i] = 0;
   __syncthreads();
   const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
-  O acc_or = 0, acc_nand = 0;
+  O acc_or = 0, acc_nand = 0, acc_max = 0, acc_nmin = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
     kt.load(a.keys, a.stride, a.n, tile, a.ko);
 #pragma unroll
     for (int i = 0; i < KT::PER_THREAD; i++)
-      if ((kt.valid >> i) & 1) { acc_or |= kt.u[i]; acc_nand |= ~kt.u[i]; }
+      if ((kt.valid >> i) & 1) {
+        acc_or |= kt.u[i];
+        acc_nand |= ~kt.u[i];
+        acc_max = kt.u[i] > acc_max ? kt.u[i] : acc_max;
+        acc_nmin = (O)~kt.u[i] > acc_nmin ? (O)~kt.u[i] : acc_nmin;
+      }
     // every CTA samples every sample-th of ITS OWN tiles (tile % sample would pile all sampled tiles on
     // 1/sample of the CTAs when the grid size is a multiple of sample)
     if (((tile / gridDim.x) + blockIdx.x) % a.sample == 0) {
@@ -246,15 +257,21 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
       }
     }
   }
-  unsigned long long o = acc_or, na = acc_nand;
+  constexpr unsigned long long KEYMASK = KB == 8 ? ~0ull : ((1ull << (8 * (KB & 7))) - 1);
+  unsigned long long o = acc_or, na = acc_nand & KEYMASK, mx = acc_max, nm = acc_nmin & KEYMASK;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     o |= __shfl_xor_sync(0xffffffffu, o, s);
     na |= __shfl_xor_sync(0xffffffffu, na, s);
+    const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, s), n2 = __shfl_xor_sync(0xffffffffu, nm, s);
+    mx = m2 > mx ? m2 : mx;
+    nm = n2 > nm ? n2 : nm;
   }
   if ((threadIdx.x & 31) == 0) {
     atomicOr(&a.probe->or_bits, o);
     atomicOr(&a.probe->nand_bits, na);
+    atomicMax(&a.probe->max_key, mx);
+    atomicMax(&a.probe->nmin_key, nm);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) {
@@ -272,13 +289,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hist_kernel(HistArgs 
   if (f == 0) return;  // nothing will be swept
   const int shift = (int)(f - 1) * RADIX_BITS;
   const bool skewed = a.plan->skewed[f - 1] != 0;
+  KeyOrder ko = a.ko;
+  ko.sub = a.plan->sub;
   __shared__ uint32_t sh[RADIX];
   for (int i = threadIdx.x; i < RADIX; i += THREADS) sh[i] = 0;
   __syncthreads();
   const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
-    kt.load(a.keys, a.stride, a.n, tile, a.ko);
+    kt.load(a.keys, a.stride, a.n, tile, ko);
     if (skewed) {
 #pragma unroll
       for (int i = 0; i < KT::PER_THREAD; i++) {
@@ -313,6 +332,7 @@ struct ScanArgs {
   int n_passes;            // = key bytes; pass p sweeps digit position p
   int allow_skip;
   int hybrid;              // 1: choose cut_digit (MSB hybrid)
+  int allow_reduce;        // 1: range reduction allowed
   float margin_bits;       // hybrid: sweep top digits until their entropies sum to log2(n) + margin_bits
 };
 
@@ -364,6 +384,26 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
       if (saved < 2) cut = 0;
       for (uint32_t p = 0; p < cut; p++) s_skip[p] = 1;
     }
+    // Range reduction: if the keys span fewer digit positions than the plan above would sweep, subtract
+    // the smallest key and sweep just those low digit positions (every digit above them is then zero).
+    unsigned long long sub = 0;
+    {
+      const unsigned long long kmask = a.n_passes >= 8 ? ~0ull : ((1ull << (8 * a.n_passes)) - 1);
+      const unsigned long long mn = (~a.probe->nmin_key) & kmask, mx = a.probe->max_key;
+      const unsigned long long range = mx - mn;
+      const int rb = range == 0 ? 0 : (63 - __clzll((long long)range)) / RADIX_BITS + 1;
+      uint32_t planned = cut ? 1 : 0;  // the finish costs about a pass
+      for (int p = 0; p < a.n_passes; p++) planned += s_skip[p] ? 0 : 1;
+      if (a.allow_reduce && mn != 0 && (uint32_t)rb < planned) {
+        sub = mn;
+        cut = 0;
+        for (int p = 0; p < a.n_passes; p++) {
+          s_skip[p] = p >= rb ? 1 : 0;
+          s_entropy[p] = 0.f;  // unknown for the shifted keys: treat every digit as skewed (safe)
+        }
+      }
+    }
+    a.plan->sub = sub;
     uint32_t sel = 0, n_exec = 0;
     int prev = -1;
     a.plan->first_exec_p1 = 0;
@@ -413,6 +453,11 @@ struct SweepArgs {
   // top lut_bits bits of the ordered key (lut has 2^lut_bits entries), not a radix digit
   const uint8_t *lut;
   int lut_shift;
+  uint32_t spin_ns;        // look-back back-off (option "spin_ns"), 0 = busy poll
+  // When the host has read the plan back (large sorts) it passes what this pass needs as arguments, so a
+  // CTA does not start with a dependent global load (244 K CTAs per pass at 1e9 records).
+  uint32_t plan_in_args, arg_sel, arg_next_p1, arg_next_skewed;
+  unsigned long long arg_sub;
 };
 
 // Per-pass constants that make the digit a handful of 32-bit operations: because the order mapping is
@@ -541,28 +586,62 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
   for (int r = 0; r < IPT; r++)
     raw[r] = (FULL || idx0 + r * 32 < n_valid) ? *reinterpret_cast<const KeyT *>(kp + (size_t)(r * 32) * key_stride) : (KeyT)0;
-  // The digit of item r is recomputed where it is needed instead of being kept in IPT registers.
-  const DigitX dx = make_digitx(a.ko, a.shift);
-  auto digit_of = [&](int r) -> uint32_t {
+  // Digits are computed once and kept packed four to a register (IPT/4 registers).
+  KeyOrder ko = a.ko;
+  ko.sub = LUT ? 0ull : (a.plan_in_args ? a.arg_sub : a.plan->sub);
+  const bool has_sub = ko.sub != 0;  // range reduction active: the xor shortcut of fast_digit does not apply
+  static_assert(IPT % 4 == 0, "digits are packed four per register");
+  uint32_t dpack[IPT / 4];
+  {
+    const DigitX dx = make_digitx(ko, a.shift);
     // padding of the last tile ranks behind everything (digit 255, last in index order)
-    if (!FULL && idx0 + r * 32 >= n_valid) return RADIX - 1;
-    if constexpr (LUT) return lut_digit<KB>(raw[r], a);  // multi-GPU partition pass
-    else return fast_digit<KB>(raw[r], dx);
-  };
+    auto pad = [&](int r, uint32_t d) -> uint32_t { return (!FULL && idx0 + r * 32 >= n_valid) ? (uint32_t)(RADIX - 1) : d; };
+    if constexpr (LUT) {
+#pragma unroll
+      for (int q = 0; q < IPT / 4; q++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          w |= pad(4 * q + e, a.lut[(uint32_t)(to_ordered<KB>(raw[4 * q + e], ko) >> a.lut_shift)]) << (8 * e);  // partition pass
+        dpack[q] = w;
+      }
+    } else if (has_sub) {
+#pragma unroll
+      for (int q = 0; q < IPT / 4; q++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          w |= pad(4 * q + e, (uint32_t)(to_ordered<KB>(raw[4 * q + e], ko) >> a.shift) & (RADIX - 1)) << (8 * e);
+        dpack[q] = w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < IPT / 4; q++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) w |= pad(4 * q + e, fast_digit<KB>(raw[4 * q + e], dx)) << (8 * e);
+        dpack[q] = w;
+      }
+    }
+  }
+  auto digit_of = [&](int r) -> uint32_t { return (dpack[r >> 2] >> (8 * (r & 3))) & (RADIX - 1); };
 
   // ---- rank inside the warp (stable) -----------------------------------------------------------------
   uint32_t rank[IPT];
   uint32_t *wc = warp_cnt + warp * RADIX;
   // the pass executed after this one gets its exact digit histogram from here (keys are in registers)
-  const uint32_t next_p1 = LUT ? 0u : a.plan->next_exec_p1[a.pass];
+  const uint32_t next_p1 = LUT ? 0u : (a.plan_in_args ? a.arg_next_p1 : a.plan->next_exec_p1[a.pass]);
   if (next_p1 != 0) {
-    const DigitX dn = make_digitx(a.ko, (int)(next_p1 - 1) * RADIX_BITS);
-    if (a.plan->skewed[next_p1 - 1]) {
+    const int nshift = (int)(next_p1 - 1) * RADIX_BITS;
+    const DigitX dn = make_digitx(ko, nshift);
+    const bool skewed = (a.plan_in_args ? a.arg_next_skewed : a.plan->skewed[next_p1 - 1]) != 0;
+    if (has_sub || skewed) {
 #pragma unroll
       for (int r = 0; r < IPT; r++) {
         const bool valid = FULL || idx0 + r * 32 < n_valid;
         const unsigned vmask = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
-        if (valid) hist_add<false>(nhist, fast_digit<KB>(raw[r], dn), vmask);
+        const uint32_t dnext = has_sub ? (uint32_t)(to_ordered<KB>(raw[r], ko) >> nshift) & (RADIX - 1) : fast_digit<KB>(raw[r], dn);
+        if (valid) hist_add<false>(nhist, dnext, vmask);
       }
     } else {
 #pragma unroll
@@ -718,7 +797,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           }
         }
         t -= consumed;
-        if (consumed == 0) __nanosleep(40);  // nothing published yet: do not burn issue slots the other CTAs need
+        if (consumed == 0 && a.spin_ns != 0) __nanosleep(a.spin_ns);  // optional back-off while nothing is published
       }
       st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
     }
@@ -770,8 +849,8 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
-  if (a.plan->skip[a.pass]) return;
-  const uint32_t sel = a.plan->src_sel[a.pass];
+  if (!a.plan_in_args && a.plan->skip[a.pass]) return;
+  const uint32_t sel = a.plan_in_args ? a.arg_sel : a.plan->src_sel[a.pass];
 
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * TILE * a.stage_bytes);

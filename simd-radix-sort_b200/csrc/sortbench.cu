@@ -187,6 +187,7 @@ int main(int argc, char **argv) {
   b200sort_stats st{};
   b200sort_last_stats(&st);
   const double avg = total / iters;
+  if (st.segfix_passes) printf("  segfix moved %llu records (%.2f %%)\n", (unsigned long long)st.segfix_moved, 100.0 * st.segfix_moved / (double)n);
   printf("key=%s pay=%zu rec=%zuB n=%lld dist=%d algo=%u passes=%u hist=%u launches=%u | best %.3f ms avg %.3f ms | %.3f Gelem/s | alg %.1f GB -> %.1f GB/s | floor(2NR) %.1f GB/s %s\n",
          key.c_str(), pay.size(), rec, (long long)n, dist, st.algo, st.passes_planned, st.hist_sweeps, st.kernel_launches, best, avg,
          n / avg * 1e-6, st.algorithmic_bytes * 1e-9, st.algorithmic_bytes / avg * 1e-6, 2.0 * n * rec / avg * 1e-6, rc_all ? "FAILED" : "ok");
