@@ -409,7 +409,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       if (have_plan) { fa.plan_in_args = 1; fa.arg_cut = hplan.cut_digit; fa.arg_sel = hplan.final_sel; fa.arg_sub = hplan.sub; }
       bool any = false;
       for (int s = 0; s < ss.n_streams; s++) any = any || ss.streams[s].chunk_bytes < 4;
-      const unsigned grid = (unsigned)((n + SF_FT - 1) / SF_FT);
+      const unsigned grid = (unsigned)std::min<int64_t>((n + SF_FT - 1) / SF_FT, (int64_t)di.sm_count * 16);
       {
         ProfScope ps(PK_SEGFIX, stream);
         if (any) segfix_kernel<8, true><<<grid, SF_THREADS, 0, stream>>>(fa);

@@ -84,8 +84,11 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   O *wkey = s_wkey[warp];
   uint16_t *q_p = s_qp[warp], *q_d = s_qd[warp];
-  const int64_t s0 = ((int64_t)blockIdx.x * SF_WARPS + warp) * SF_CHUNK;
-  if (s0 >= a.n) return;
+  // every warp walks over chunks with a grid-wide stride: a few long-lived CTAs instead of one CTA per
+  // 2048 keys (488 K CTA launches at 1e9 records cost more than the work itself)
+  const int64_t n_chunks = (a.n + SF_CHUNK - 1) / SF_CHUNK;
+  for (int64_t chunk = (int64_t)blockIdx.x * SF_WARPS + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * SF_WARPS) {
+  const int64_t s0 = chunk * SF_CHUNK;
   const int64_t e0 = s0 + SF_CHUNK < a.n ? s0 + SF_CHUNK : a.n;
   const int64_t w0 = s0 - SF_HALO > 0 ? s0 - SF_HALO : 0;
   const int64_t w1 = e0 + SF_HALO < a.n ? e0 + SF_HALO : a.n;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
   }
   if (__any_sync(0xffffffffu, fail) && lane == 0) atomicOr(&a.ctrl->flags[0], 1u);
   __syncwarp();
-  if (q_count == 0) return;
+  if (q_count == 0) continue;
   if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ctrl->flags[2]), (unsigned long long)q_count);  // statistics
 
   // ---- move every stream: window position q_p -> q_d (side `sel` -> side 0) -------------------------------
@@ -198,6 +201,8 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
       }
     }
   }
+  __syncwarp();  // the warp's scratch is reused by its next chunk
+  }  // chunk loop
 }
 
 }  // namespace b200sort
