@@ -38,6 +38,7 @@ static std::atomic<int64_t> opt_use_match{0};
 static std::atomic<int64_t> opt_allow_skip{1};
 static std::atomic<int64_t> opt_allow_reduce{1};
 static std::atomic<int64_t> opt_spin_ns{0};
+static std::atomic<int64_t> opt_fix_in_pass{1};  // order tile-local segments in the last pass + junction fix instead of the full finish
 static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 
@@ -110,9 +111,10 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
-static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1) {
+static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false) {
   const size_t tile = (size_t)c.threads * c.ipt;
-  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 + RADIX * 4;
+  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 + RADIX * 4 +
+         (fix ? tile * 3 : 0);  // FIX: slot -> item map + list of run heads
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
@@ -133,15 +135,16 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
     nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * tc.minb <= smem_optin + 1024) ? 2 : 1;
   if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2) > smem_optin) nstage = 1;
   const bool lut = a.lut != nullptr;
-  if (lut) nstage = 1;
+  const bool fix = !lut && a.fix_cut != 0;  // (the caller only sets fix_cut where the FIX instantiation exists)
+  if (lut || fix) nstage = 1;
   SweepFn k;
   switch (kb) {
-    case 1: k = sweep_fn_kb1(cfg, nstage, any, lut); break;
-    case 2: k = sweep_fn_kb2(cfg, nstage, any, lut); break;
-    case 4: k = sweep_fn_kb4(cfg, nstage, any, lut); break;
-    default: k = sweep_fn_kb8(cfg, nstage, any, lut); break;
+    case 1: k = sweep_fn_kb1(cfg, nstage, any, lut, fix); break;
+    case 2: k = sweep_fn_kb2(cfg, nstage, any, lut, fix); break;
+    case 4: k = sweep_fn_kb4(cfg, nstage, any, lut, fix); break;
+    default: k = sweep_fn_kb8(cfg, nstage, any, lut, fix); break;
   }
-  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage);
+  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
@@ -389,6 +392,13 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
 
     if (have_plan) CUDA_TRY(cudaEventSynchronize(plan_event));
     const int64_t n_tiles = (n + tile - 1) / tile;
+    HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
+    // With the plan on the host, an 8-byte-key SoA sort lets the LAST pass order the final segments each tile
+    // holds and repairs the tile-straddling ones with junction_fix_kernel; the full segment finish then only
+    // runs if one of them reports a run that is too long.
+    const bool soa = streams[0].elem_bytes == (uint32_t)kb;
+    const bool use_fix = have_plan && hplan.cut_digit != 0 && soa && cfg == 1 && opt_fix_in_pass.load() != 0;
+    int last_pass = -1;
     for (int p = 0; p < kb; p++) {
       if (have_plan && hplan.skip[p]) continue;
       SweepArgs wa{};
@@ -399,11 +409,11 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       if (have_plan) {
         wa.plan_in_args = 1; wa.arg_sel = hplan.src_sel[p]; wa.arg_next_p1 = hplan.next_exec_p1[p];
         wa.arg_next_skewed = hplan.next_exec_p1[p] ? hplan.skewed[hplan.next_exec_p1[p] - 1] : 0; wa.arg_sub = hplan.sub;
+        if (use_fix && hplan.next_exec_p1[p] == 0) { wa.fix_cut = hplan.cut_digit; wa.fix_flag = &ctrl->flags[1]; last_pass = p; }
       }
       CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream));
     }
-    HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
-    if (hybrid && !(have_plan && hplan.cut_digit == 0)) {
+    auto launch_segfix = [&]() -> int {
       SegfixArgs fa{};
       fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl;
       if (have_plan) { fa.plan_in_args = 1; fa.arg_cut = hplan.cut_digit; fa.arg_sel = hplan.final_sel; fa.arg_sub = hplan.sub; }
@@ -417,15 +427,47 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       }
       g_launches++;
       CUDA_TRY(cudaGetLastError());
+      return 0;
+    };
+    auto launch_copyback = [&](bool force) -> int {
+      CopyBackArgs ca{};
+      ca.ss = ss; ca.n = n; ca.plan = plan; ca.force = force ? 1 : 0;
+      {
+        ProfScope ps(PK_COPYBACK, stream);
+        copyback_kernel<<<di.sm_count * 8, 256, 0, stream>>>(ca);
+      }
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    };
+    bool finish_ran = false;
+    if (last_pass >= 0) {
+      JunctionArgs ja{};
+      ja.ss = ss; ja.n = n; ja.ko = ko; ja.ko.sub = hplan.sub; ja.lookback = lookback; ja.n_tiles = n_tiles;
+      ja.tag = (uint32_t)(last_pass + 1); ja.cut = hplan.cut_digit; ja.sel = hplan.final_sel; ja.flag = &ctrl->flags[1];
+      const int64_t threads = n_tiles * RADIX;
+      {
+        ProfScope ps(PK_SEGFIX, stream);
+        junction_fix_kernel<8><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(ja);
+      }
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      HybridCtrl h1{};
+      CUDA_TRY(cudaMemcpyAsync(&h1, ctrl, sizeof h1, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      if (h1.flags[1] != 0) {  // a run too long for the on-the-fly path: the full finish repairs everything
+        if (int rc = launch_segfix()) return rc;
+        finish_ran = true;
+      } else if (hplan.final_sel == 1) {
+        if (int rc = launch_copyback(true)) return rc;
+      }
+    } else {
+      if (hybrid && !(have_plan && hplan.cut_digit == 0)) {
+        if (int rc = launch_segfix()) return rc;
+        finish_ran = true;
+      }
+      if (int rc = launch_copyback(false)) return rc;
     }
-    CopyBackArgs ca{};
-    ca.ss = ss; ca.n = n; ca.plan = plan;
-    {
-      ProfScope ps(PK_COPYBACK, stream);
-      copyback_kernel<<<di.sm_count * 8, 256, 0, stream>>>(ca);
-    }
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
     stt.passes_planned = (uint32_t)kb;
     stt.hist_sweeps = 2;  // probe + exact histogram of the first pass
     stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
@@ -437,7 +479,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       CUDA_TRY(cudaMemcpyAsync(&hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
       stt.passes_planned = hplan.n_exec;
-      stt.segfix_passes = hplan.cut_digit != 0 ? 1 : 0;
+      stt.segfix_passes = finish_ran ? 1 : 0;
       stt.cut_digit = hplan.cut_digit;
       memcpy(&stt.segfix_moved, &hctrl.flags[2], 8);
       stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
@@ -628,6 +670,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "allow_reduce")) return &opt_allow_reduce;
   if (!strcmp(name, "spin_ns")) return &opt_spin_ns;
+  if (!strcmp(name, "fix_in_pass")) return &opt_fix_in_pass;
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;

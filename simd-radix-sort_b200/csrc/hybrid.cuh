@@ -205,4 +205,89 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
   }  // chunk loop
 }
 
+// ------------------------------------------------------------------------------------------------
+// Junction fix: companion of the FIX instantiation of onesweep_kernel.  The last pass has put every
+// final segment in order as far as one tile held it; what can still be out of order are segments whose
+// keys came from two (or more) consecutive tiles.  In the output such a segment lies across a "junction":
+// the place inside a bucket where the contribution of tile t ends and that of tile t+1 begins -- and that
+// place is exactly the inclusive prefix that tile t published in the look-back table of the last pass.
+// One thread per (tile, digit) looks at the two keys around its junction; if they agree on all swept bits
+// it orders the (short) segment there, all streams included.  A segment longer than JF_CAP raises the flag
+// that makes the host run the full segment finish.
+// ------------------------------------------------------------------------------------------------
+constexpr int JF_CAP = 32;
+
+struct JunctionArgs {
+  StreamSet ss;
+  int64_t n;
+  KeyOrder ko;               // with the plan's range reduction already applied by the host
+  const uint64_t *lookback;  // [n_tiles][RADIX] status words of the last executed pass
+  int64_t n_tiles;
+  uint32_t tag;              // generation tag of that pass
+  uint32_t cut, sel;         // Plan::cut_digit, side holding the data
+  uint32_t *flag;            // raised when a segment is too long for this kernel
+};
+
+template <typename T>
+__device__ __forceinline__ void junction_permute(unsigned char *buf, int64_t lo, int len, const uint8_t *src_of, uint32_t cpe, uint32_t c) {
+  T *d = reinterpret_cast<T *>(buf) + (size_t)lo * cpe + c;
+  T tmp[JF_CAP];
+  for (int x = 0; x < len; x++) tmp[x] = d[(size_t)x * cpe];
+  for (int x = 0; x < len; x++) d[(size_t)x * cpe] = tmp[src_of[x]];
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256) junction_fix_kernel(const __grid_constant__ JunctionArgs a) {
+  using O = typename OrdOf<KB>::type;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = idx / RADIX;
+  const int d = (int)(idx % RADIX);
+  if (t >= a.n_tiles - 1) return;  // the last tile has no successor
+  const int64_t g = (int64_t)(a.lookback[(size_t)t * RADIX + d] & LB_VALUE_MASK);          // end of tile t's part
+  const int64_t g_end = (int64_t)(a.lookback[(size_t)(a.n_tiles - 1) * RADIX + d] & LB_VALUE_MASK);  // bucket end
+  if (g >= g_end) return;          // nothing of this bucket follows
+  const int64_t g_prev = t > 0 ? (int64_t)(a.lookback[(size_t)(t - 1) * RADIX + d] & LB_VALUE_MASK) : -1;
+  if (t > 0 && g == g_prev) return;  // tile t put nothing here: the junction coincides with an earlier one
+  if (g <= 0) return;
+
+  const Stream &ks = a.ss.streams[0];
+  const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
+  unsigned char *kbuf = ks.buf[a.sel];
+  const O pmask = (O)(~(O)0) << (8 * a.cut);
+  auto okey = [&](int64_t i) -> O { return to_ordered<KB>(load_key<KB>(kbuf, i, key_stride), a.ko); };
+  const O k0 = okey(g - 1);
+  if (((k0 ^ okey(g)) & pmask) != 0) return;  // the common case: different segments on either side
+  int64_t lo = g - 1, hi = g + 1;
+  while (lo > 0 && g - lo <= JF_CAP && ((okey(lo - 1) ^ k0) & pmask) == 0) lo--;
+  while (hi < a.n && hi - g <= JF_CAP && ((okey(hi) ^ k0) & pmask) == 0) hi++;
+  const int len = (int)(hi - lo);
+  if (len > JF_CAP) { atomicOr(a.flag, 1u); return; }
+  if (t > 0 && lo < g_prev) return;  // an earlier junction lies inside this segment: its thread orders it
+
+  // rank counting on the full key -> source of every destination slot, then permute every stream
+  O keys[JF_CAP];
+  uint8_t src_of[JF_CAP];
+  for (int x = 0; x < len; x++) keys[x] = okey(lo + x);
+  bool moved = false;
+  for (int x = 0; x < len; x++) {
+    int r = 0;
+    for (int y = 0; y < len; y++) r += (keys[y] < keys[x] || (keys[y] == keys[x] && y < x)) ? 1 : 0;
+    src_of[r] = (uint8_t)x;
+    moved = moved || r != x;
+  }
+  if (!moved) return;
+  for (int s = 0; s < a.ss.n_streams; s++) {
+    const Stream &st = a.ss.streams[s];
+    for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
+      switch (st.chunk_bytes) {
+        case 1: junction_permute<uint8_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+        case 2: junction_permute<uint16_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+        case 4: junction_permute<uint32_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+        case 8: junction_permute<uint64_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+        default: junction_permute<uint4>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+      }
+    }
+  }
+}
+
 }  // namespace b200sort

@@ -458,7 +458,13 @@ struct SweepArgs {
   // CTA does not start with a dependent global load (244 K CTAs per pass at 1e9 records).
   uint32_t plan_in_args, arg_sel, arg_next_p1, arg_next_skewed;
   unsigned long long arg_sub;
+  // FIX instantiation (last pass of the MSB hybrid plan): Plan::cut_digit and where to report a run of
+  // more than FIX_CAP keys that agree on all swept bits (the full segment finish then has to run)
+  uint32_t fix_cut;
+  uint32_t *fix_flag;
 };
+
+constexpr int FIX_CAP = 16;  // longest run of keys agreeing on all swept bits that is ordered on the fly
 
 // Per-pass constants that make the digit a handful of 32-bit operations: because the order mapping is
 // an xor, digit(ordered key) = digit(raw key) ^ digit(xor_const) ^ (negative ? digit(neg_xor) : 0).
@@ -557,7 +563,7 @@ __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned cha
   }
 }
 
-template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FULL>
+template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
                                            const uint32_t sel) {
   constexpr int TILE = THREADS * IPT;
@@ -572,6 +578,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
   uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
   uint32_t *nhist = reinterpret_cast<uint32_t *>(sdigit + TILE);                             // RADIX (zeroed by the kernel)
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(nhist + RADIX);                              // TILE (FIX only): slot -> item
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile_base = tile * TILE;
@@ -760,7 +767,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     KeyT *kst = reinterpret_cast<KeyT *>(bufs[0]);
 #pragma unroll
     for (int r = 0; r < IPT; r++)
-      if (FULL || idx0 + r * 32 < n_valid) kst[rank[r]] = raw[r];
+      if (FULL || idx0 + r * 32 < n_valid) {
+        kst[rank[r]] = raw[r];
+        if (FIX) sidx[rank[r]] = (uint16_t)(idx0 + r * 32);
+      }
   } else {
     issue_next(bufs[0]);
   }
@@ -806,6 +816,111 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
   __syncthreads();  // column 0, sdigit and gbase visible to everyone
 
+  __shared__ int s_fix_heads;
+  if constexpr (FIX) {
+    // Last pass of the MSB hybrid plan.  In bucket order, the tile's keys that agree on ALL swept bits
+    // (>= 8*fix_cut) are adjacent: within a bucket they are still ordered by the lower swept digits.  Such a
+    // run is one final segment as far as this tile holds it, so it is put in full-key order here, while the
+    // keys sit in shared memory (staged slots are walked in order: neighbours come from a shuffle).  Only
+    // segments that straddle two tiles are left for junction_fix_kernel.
+    if (soa_keys) {
+      using O = typename OrdOf<KB>::type;
+      KeyT *kst = reinterpret_cast<KeyT *>(bufs[0]);
+      const O pmask = (O)(~(O)0) << (8 * a.fix_cut);
+      // phase 1: walk the staged slots in order and collect the first slot of every run of >= 2 keys that
+      // share all swept bits (neighbours come from shuffles; a divergent repair right here would be paid
+      // by every warp row, because almost every row of 32 slots holds at least one such run)
+      uint16_t *hlist = sidx + TILE;  // up to TILE/2 run heads
+      if (tid == 0) s_fix_heads = 0;
+      __syncthreads();
+      // (equal swept bits of the ordered keys <=> equal swept bits of the raw keys: the order mapping is an xor
+      //  whose only key-dependent part is the sign bit, itself a swept bit; no range reduction is active when a
+      //  cut exists.  For a cut at or above bit 32 only the high word has to travel through the shuffles.)
+      const bool hi_only = a.fix_cut >= 4;
+#pragma unroll 1
+      for (int k = 0; k < IPT; k++) {
+        const int i = tid + k * THREADS;
+        const bool valid = i < n_valid;
+        const O pk = valid ? ((O)kst[i] & pmask) : (O)0;
+        O pn;
+        if (hi_only) pn = (O)__shfl_down_sync(0xffffffffu, (uint32_t)(pk >> 32), 1) << 32;
+        else pn = __shfl_down_sync(0xffffffffu, pk, 1);
+        bool vn = __shfl_down_sync(0xffffffffu, (int)valid, 1) != 0;
+        if (lane == 31) {
+          vn = i + 1 < n_valid;
+          pn = vn ? ((O)kst[i + 1] & pmask) : (O)0;
+        }
+        const bool same_next = valid && vn && pk == pn;
+        bool same_prev = __shfl_up_sync(0xffffffffu, (int)same_next, 1) != 0;
+        if (lane == 0) same_prev = valid && i > 0 && ((O)kst[i - 1] & pmask) == pk;
+        const bool head = same_next && !same_prev;
+        const unsigned hm = __ballot_sync(0xffffffffu, head);
+        if (hm) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_fix_heads, __popc(hm));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (head) hlist[base + __popc(hm & lanemask_lt())] = (uint16_t)i;
+        }
+      }
+      __syncthreads();
+      // phase 2: one thread per run.  Runs are almost always 2 keys, rarely 3 or 4: ordered by a 4-element
+      // network in registers; longer ones serially; more than FIX_CAP keys: left to the full finish.
+      const int n_heads = s_fix_heads;
+      for (int h = tid; h < n_heads; h += THREADS) {
+        const int i = hlist[h];
+        const O ki = to_ordered<KB>(kst[i], ko);
+        int len = 2;
+        while (len <= FIX_CAP && i + len < n_valid && ((to_ordered<KB>(kst[i + len], ko) ^ ki) & pmask) == 0) len++;
+        if (len > FIX_CAP) {
+          atomicOr(a.fix_flag, 1u);
+        } else if (len <= 4) {
+          KeyT r[4];
+          O o[4];
+          uint32_t sx[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) {
+            r[x] = x < len ? kst[i + x] : (KeyT)0;
+            sx[x] = x < len ? sidx[i + x] : 0u;
+            o[x] = x < len ? to_ordered<KB>(r[x], ko) : (O)~(O)0;  // padding sorts last and stays in place
+          }
+          auto cx = [&](int p, int q) {  // compare-exchange
+            if (o[q] < o[p]) {
+              const O to = o[p]; o[p] = o[q]; o[q] = to;
+              const KeyT tr = r[p]; r[p] = r[q]; r[q] = tr;
+              const uint32_t ts = sx[p]; sx[p] = sx[q]; sx[q] = ts;
+            }
+          };
+          cx(0, 1); cx(2, 3); cx(0, 2); cx(1, 3); cx(1, 2);
+#pragma unroll
+          for (int x = 0; x < 4; x++) {
+            if (x < len) {
+              kst[i + x] = r[x];
+              sidx[i + x] = (uint16_t)sx[x];
+              srank[sx[x]] = (uint16_t)(i + x);  // payload columns follow the corrected slots
+            }
+          }
+        } else {
+          const int e = i + len;
+          for (int x = i + 1; x < e; x++) {  // insertion sort of the run, slot -> item map carried along
+            const KeyT kx = kst[x];
+            const O ox = to_ordered<KB>(kx, ko);
+            const uint16_t s1 = sidx[x];
+            int y = x;
+            while (y > i && to_ordered<KB>(kst[y - 1], ko) > ox) {
+              kst[y] = kst[y - 1];
+              sidx[y] = sidx[y - 1];
+              y--;
+            }
+            kst[y] = kx;
+            sidx[y] = s1;
+          }
+          for (int x = i; x < e; x++) srank[sidx[x]] = (uint16_t)x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
   int64_t goff[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
@@ -844,7 +959,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
 // ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
 // far more registers per thread, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT>
+template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX = false>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
@@ -867,9 +982,9 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
   if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, true>(a, smem, tile, TILE, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, true>(a, smem, tile, TILE, sel);
   else
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, false>(a, smem, tile, (int)remaining, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, false>(a, smem, tile, (int)remaining, sel);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -879,10 +994,11 @@ struct CopyBackArgs {
   StreamSet ss;
   int64_t n;
   const Plan *plan;
+  int force;  // 1: the host knows the result is in the shadow (no finish kernel delivered it)
 };
 
 static __global__ void __launch_bounds__(256) copyback_kernel(const __grid_constant__ CopyBackArgs a) {
-  if (a.plan->final_sel == 0 || a.plan->cut_digit != 0) return;  // (the segment finish already wrote side 0)
+  if (!a.force && (a.plan->final_sel == 0 || a.plan->cut_digit != 0)) return;  // (the segment finish already wrote side 0)
   for (int s = 0; s < a.ss.n_streams; s++) {
     const Stream &st = a.ss.streams[s];
     const size_t bytes = (size_t)a.n * st.chunk_bytes * st.chunks_per_elem;

@@ -1,5 +1,5 @@
 // onesweep_kernel instantiations for 8-byte keys (see sweep_select.cuh)
 #include "sweep_select.cuh"
 namespace b200sort {
-SweepFn sweep_fn_kb8(int cfg, int nstage, bool any, bool lut) { return sweep_fn<8>(cfg, nstage, any, lut); }
+SweepFn sweep_fn_kb8(int cfg, int nstage, bool any, bool lut, bool fix) { return sweep_fn<8>(cfg, nstage, any, lut, fix); }
 }  // namespace b200sort
