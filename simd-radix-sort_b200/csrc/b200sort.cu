@@ -114,7 +114,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false) {
   const size_t tile = (size_t)c.threads * c.ipt;
   return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 + RADIX * 4 +
-         (fix ? tile * 3 : 0);  // FIX: slot -> item map + list of run heads
+         (fix ? tile : 0);  // FIX: per-slot displacement
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns

@@ -578,7 +578,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
   uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
   uint32_t *nhist = reinterpret_cast<uint32_t *>(sdigit + TILE);                             // RADIX (zeroed by the kernel)
-  uint16_t *sidx = reinterpret_cast<uint16_t *>(nhist + RADIX);                              // TILE (FIX only): slot -> item
+  int8_t *sdelta = reinterpret_cast<int8_t *>(nhist + RADIX);                                // TILE (FIX only): slot displacement
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile_base = tile * TILE;
@@ -769,7 +769,6 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     for (int r = 0; r < IPT; r++)
       if (FULL || idx0 + r * 32 < n_valid) {
         kst[rank[r]] = raw[r];
-        if (FIX) sidx[rank[r]] = (uint16_t)(idx0 + r * 32);
       }
   } else {
     issue_next(bufs[0]);
@@ -816,106 +815,87 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
   __syncthreads();  // column 0, sdigit and gbase visible to everyone
 
-  __shared__ int s_fix_heads;
   if constexpr (FIX) {
     // Last pass of the MSB hybrid plan.  In bucket order, the tile's keys that agree on ALL swept bits
     // (>= 8*fix_cut) are adjacent: within a bucket they are still ordered by the lower swept digits.  Such a
     // run is one final segment as far as this tile holds it, so it is put in full-key order here, while the
-    // keys sit in shared memory (staged slots are walked in order: neighbours come from a shuffle).  Only
-    // segments that straddle two tiles are left for junction_fix_kernel.
+    // keys sit in shared memory.  Nothing is moved in shared memory: every member of a run computes where it
+    // belongs inside the run and leaves the displacement in sdelta[slot]; the destination offsets of ALL
+    // columns (goff, below) pick it up.  Only segments that straddle two tiles are left for
+    // junction_fix_kernel.
     if (soa_keys) {
       using O = typename OrdOf<KB>::type;
-      KeyT *kst = reinterpret_cast<KeyT *>(bufs[0]);
+      const KeyT *kst = reinterpret_cast<const KeyT *>(bufs[0]);
       const O pmask = (O)(~(O)0) << (8 * a.fix_cut);
-      // phase 1: walk the staged slots in order and collect the first slot of every run of >= 2 keys that
-      // share all swept bits (neighbours come from shuffles; a divergent repair right here would be paid
-      // by every warp row, because almost every row of 32 slots holds at least one such run)
-      uint16_t *hlist = sidx + TILE;  // up to TILE/2 run heads
-      if (tid == 0) s_fix_heads = 0;
-      __syncthreads();
-      // (equal swept bits of the ordered keys <=> equal swept bits of the raw keys: the order mapping is an xor
-      //  whose only key-dependent part is the sign bit, itself a swept bit; no range reduction is active when a
-      //  cut exists.  For a cut at or above bit 32 only the high word has to travel through the shuffles.)
-      const bool hi_only = a.fix_cut >= 4;
-#pragma unroll 1
-      for (int k = 0; k < IPT; k++) {
-        const int i = tid + k * THREADS;
-        const bool valid = i < n_valid;
-        const O pk = valid ? ((O)kst[i] & pmask) : (O)0;
-        O pn;
-        if (hi_only) pn = (O)__shfl_down_sync(0xffffffffu, (uint32_t)(pk >> 32), 1) << 32;
-        else pn = __shfl_down_sync(0xffffffffu, pk, 1);
-        bool vn = __shfl_down_sync(0xffffffffu, (int)valid, 1) != 0;
-        if (lane == 31) {
-          vn = i + 1 < n_valid;
-          pn = vn ? ((O)kst[i + 1] & pmask) : (O)0;
-        }
-        const bool same_next = valid && vn && pk == pn;
-        bool same_prev = __shfl_up_sync(0xffffffffu, (int)same_next, 1) != 0;
-        if (lane == 0) same_prev = valid && i > 0 && ((O)kst[i - 1] & pmask) == pk;
-        const bool head = same_next && !same_prev;
-        const unsigned hm = __ballot_sync(0xffffffffu, head);
-        if (hm) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s_fix_heads, __popc(hm));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (head) hlist[base + __popc(hm & lanemask_lt())] = (uint16_t)i;
-        }
-      }
-      __syncthreads();
-      // phase 2: one thread per run.  Runs are almost always 2 keys, rarely 3 or 4: ordered by a 4-element
-      // network in registers; longer ones serially; more than FIX_CAP keys: left to the full finish.
-      const int n_heads = s_fix_heads;
-      for (int h = tid; h < n_heads; h += THREADS) {
-        const int i = hlist[h];
-        const O ki = to_ordered<KB>(kst[i], ko);
-        int len = 2;
-        while (len <= FIX_CAP && i + len < n_valid && ((to_ordered<KB>(kst[i + len], ko) ^ ki) & pmask) == 0) len++;
-        if (len > FIX_CAP) {
-          atomicOr(a.fix_flag, 1u);
-        } else if (len <= 4) {
-          KeyT r[4];
-          O o[4];
-          uint32_t sx[4];
+      const int base = tid * IPT;
+      const int lim = FULL ? TILE : n_valid;
 #pragma unroll
-          for (int x = 0; x < 4; x++) {
-            r[x] = x < len ? kst[i + x] : (KeyT)0;
-            sx[x] = x < len ? sidx[i + x] : 0u;
-            o[x] = x < len ? to_ordered<KB>(r[x], ko) : (O)~(O)0;  // padding sorts last and stays in place
-          }
-          auto cx = [&](int p, int q) {  // compare-exchange
-            if (o[q] < o[p]) {
-              const O to = o[p]; o[p] = o[q]; o[q] = to;
-              const KeyT tr = r[p]; r[p] = r[q]; r[q] = tr;
-              const uint32_t ts = sx[p]; sx[p] = sx[q]; sx[q] = ts;
-            }
-          };
-          cx(0, 1); cx(2, 3); cx(0, 2); cx(1, 3); cx(1, 2);
+      for (int q = 0; q < IPT / 16; q++) reinterpret_cast<uint4 *>(sdelta + base)[q] = make_uint4(0, 0, 0, 0);
+      // The thread owns slots base .. base+IPT-1 and looks at the window base-1 .. base+IPT (W = IPT+2 slots),
+      // lane l starting at window position l mod W: a warp's loads then spread over the banks although the
+      // threads' windows are IPT keys apart.  (Equal swept bits of the ordered keys <=> equal swept bits of
+      // the raw keys: the order mapping is an xor whose only key-dependent part is the sign bit, itself a
+      // swept bit, and no range reduction is active when a cut exists.  Sentinel 1 never equals a masked key.)
+      constexpr int W = IPT + 2;
+      const int rot = lane % W;
+      uint32_t eq = 0;  // bit k: window positions (k+rot)%W and (k+1+rot)%W hold equal swept bits
+      auto scan_window = [&](auto tag) {
+        using T = decltype(tag);
+        T pref[W];
 #pragma unroll
-          for (int x = 0; x < 4; x++) {
-            if (x < len) {
-              kst[i + x] = r[x];
-              sidx[i + x] = (uint16_t)sx[x];
-              srank[sx[x]] = (uint16_t)(i + x);  // payload columns follow the corrected slots
-            }
+        for (int k = 0; k < W; k++) {
+          int w = k + rot;
+          if (w >= W) w -= W;
+          const int i = base - 1 + w;
+          T v = (T)1;
+          if (i >= 0 && i < lim) {
+            if constexpr (sizeof(T) == sizeof(O)) v = (T)((O)kst[i] & pmask);
+            else v = reinterpret_cast<const uint32_t *>(kst)[2 * i + 1] & (uint32_t)((uint64_t)pmask >> 32);
           }
-        } else {
-          const int e = i + len;
-          for (int x = i + 1; x < e; x++) {  // insertion sort of the run, slot -> item map carried along
-            const KeyT kx = kst[x];
-            const O ox = to_ordered<KB>(kx, ko);
-            const uint16_t s1 = sidx[x];
-            int y = x;
-            while (y > i && to_ordered<KB>(kst[y - 1], ko) > ox) {
-              kst[y] = kst[y - 1];
-              sidx[y] = sidx[y - 1];
-              y--;
-            }
-            kst[y] = kx;
-            sidx[y] = s1;
-          }
-          for (int x = i; x < e; x++) srank[sidx[x]] = (uint16_t)x;
+          pref[k] = v;
         }
+#pragma unroll
+        for (int k = 0; k < W; k++) eq |= (uint32_t)(pref[k] == pref[(k + 1) % W]) << k;
+      };
+      if (KB == 8 && a.fix_cut >= 4) scan_window((uint32_t)0); else scan_window((O)0);
+      // re-index by window position: bit j = slots (base-1+j, base+j) agree, j = 0 .. IPT; bit W-1 is the wrap
+      eq = ((eq << rot) | (eq >> (W - rot))) & ((1u << (W - 1)) - 1u);
+      uint32_t members = (eq | (eq >> 1)) & ((1u << IPT) - 1u);  // own slots with an equal neighbour
+      if (!FULL) members &= lim - base >= IPT ? ~0u : (1u << max(lim - base, 0)) - 1u;  // sentinels are no members
+      while (members) {
+        const int sl = __ffs(members) - 1;
+        members &= members - 1;
+        const int i = base + sl;
+        const KeyT kraw = kst[i];
+        const O ok = to_ordered<KB>(kraw, ko);
+        // neighbours known to be in the run from the window bits, then (rarely) beyond the window
+        const uint32_t below = ~eq & ((2u << sl) - 1u);  // zero bits at or below sl stop the run on the left
+        int nl = below ? sl - (31 - __clz(below)) : sl + 1;
+        const uint32_t above = ~(eq >> (sl + 1));
+        int nr = __ffs(above) - 1;  // IPT - sl when the run reaches the end of the window
+        int cl = 0, cr = 0;
+        for (int q = 1; q <= nl; q++) cl += to_ordered<KB>(kst[i - q], ko) > ok;
+        for (int q = 1; q <= nr; q++) cr += to_ordered<KB>(kst[i + q], ko) < ok;
+        bool over = false;
+        if (nl == sl + 1) {  // the run includes slot base-1: it may go on further left
+          int j = i - nl - 1;
+          while (j >= 0 && (((O)kst[j] ^ (O)kraw) & pmask) == 0) {
+            if (++nl > FIX_CAP) { over = true; break; }
+            cl += to_ordered<KB>(kst[j], ko) > ok;
+            j--;
+          }
+        }
+        if (nr == IPT - sl) {  // includes slot base+IPT
+          int j = i + nr + 1;
+          while (j < lim && (((O)kst[j] ^ (O)kraw) & pmask) == 0) {
+            if (++nr > FIX_CAP) { over = true; break; }
+            cr += to_ordered<KB>(kst[j], ko) < ok;
+            j++;
+          }
+        }
+        // every member sees the same total length unless it hit the cap, so all of them agree on "too long"
+        if (over || nl + nr > FIX_CAP) atomicOr(a.fix_flag, 1u);
+        else if (cr != cl) sdelta[i] = (int8_t)(cr - cl);
       }
       __syncthreads();
     }
@@ -925,7 +905,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     const int i = tid + k * THREADS;
-    goff[k] = (FULL || i < n_valid) ? gbase[sdigit[i]] + i : 0;
+    goff[k] = (FULL || i < n_valid) ? gbase[sdigit[i]] + i + (FIX ? (int)sdelta[i] : 0) : 0;
   }
   int wr_s = 0;  // write cursor
   uint32_t wr_c = 0;

@@ -22,7 +22,8 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 // dist: 0 uniform bits, 1 few-unique (16 values -8..7 as signed), 2 zipf-ish over 2^20 ranks, 3 all zero,
-// 4 uniform float in (-1,1) (for f32/f64 keys), 5 sorted
+// 4 uniform float in (-1,1) (for f32/f64 keys), 5 sorted, 6 uniform 62-bit values (at 2^28 records the
+// same run density below a 32-bit cut as 1e9 uniform 64-bit keys)
 __global__ void fill_keys(unsigned char *keys, int kb, uint32_t stride, int64_t n, uint64_t seed, int dist, int is_float) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t r = mix64(seed + (uint64_t)i);
@@ -35,6 +36,7 @@ __global__ void fill_keys(unsigned char *keys, int kb, uint32_t stride, int64_t 
       v = mix64(rank * 0x1234567ull + 99);
     } else if (dist == 3) v = 0;
     else if (dist == 5) v = (uint64_t)i * 3;
+    else if (dist == 6) v = r >> 2;
     if (dist == 4 || is_float) {
       double u = (double)(r >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
       if (kb == 4) { float f = (float)u; memcpy(&v, &f, 4); }
