@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -41,6 +42,7 @@ static std::atomic<int64_t> opt_spin_ns{0};
 static std::atomic<int64_t> opt_fix_in_pass{1};  // order tile-local segments in the last pass + junction fix instead of the full finish
 static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
+static std::atomic<int64_t> opt_probe_guess{1};
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
 enum ProfKind { PK_HIST = 0, PK_SCAN = 1, PK_SWEEP = 2, PK_COPYBACK = 3, PK_SEGFIX = 4, PK_OTHER = 5 };
@@ -158,9 +160,11 @@ constexpr int HIST_THREADS = 256;  // key-only sweeps: 256 threads x NLD x 16 B 
 constexpr int hist_nld(int kb) { return kb == 1 ? 2 : 4; }  // at most 32 keys per thread
 
 template <int KB>
-static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, bool probe, cudaStream_t st) {
+static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, int probe, cudaStream_t st) {
   ProfScope ps(PK_HIST, st);
-  if (probe) {
+  if (probe == 2) {
+    minmax_kernel<KB, HIST_THREADS, hist_nld(KB)><<<grid, HIST_THREADS, 0, st>>>(a);
+  } else if (probe) {
     if (use_match) probe_kernel<KB, HIST_THREADS, hist_nld(KB), true><<<grid, HIST_THREADS, 0, st>>>(a);
     else probe_kernel<KB, HIST_THREADS, hist_nld(KB), false><<<grid, HIST_THREADS, 0, st>>>(a);
   } else {
@@ -171,7 +175,7 @@ static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, bo
   return cudaGetLastError();
 }
 
-cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, bool probe, cudaStream_t st) {
+cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, int probe, cudaStream_t st) {
   const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
   const int64_t tiles = (a.n + tile_keys - 1) / tile_keys;
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * 8);
@@ -353,11 +357,31 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     ha.keys = ss.streams[0].buf[0];
     ha.stride = streams[0].elem_bytes;
     ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
+    const bool big = hybrid && n >= (int64_t)1 << 24;  // the host reads the plan back
     {
       const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
-      ha.sample = (n / tile_keys) >= 8192 ? 16 : 1;  // entropies from 1/16 of the tiles once there are plenty
+      // entropies from one key per thread of every 8th tile once there are plenty of tiles
+      const bool sparse = (n / tile_keys) >= 8192;
+      ha.sample = sparse ? 8 : 1;
+      ha.sample_one = sparse ? 1 : 0;
     }
-    CUDA_TRY(launch_hist(kb, ha, di.sm_count, /*probe=*/true, stream));
+    // Large sorts leave the exact key range to a sweep of its own that only runs when the sampled range says
+    // range reduction may pay; the others get it from the probe.
+    ha.with_minmax = big ? 0 : 1;
+    // The digit position the first pass will sweep if the keys are (close to) uniformly distributed: the
+    // probe counts it exactly, and if the plan comes out that way hist_kernel is not needed.
+    {
+      uint32_t guess = 0;
+      if (hybrid) {
+        const double need = std::log2((double)n) + (double)opt_margin_bits.load();
+        const int swept = (int)std::ceil(need / 8.0);
+        const int cut = 8 - swept;
+        guess = cut >= 2 ? (uint32_t)cut : 0;
+      }
+      ha.guess_p1 = opt_probe_guess.load() != 0 ? guess + 1 : 0;
+      ha.ghist_exact = ghist_exact;
+    }
+    CUDA_TRY(launch_hist(kb, ha, di.sm_count, /*probe=*/1, stream));
 
     ScanArgs sa{};
     sa.ghist = ghist; sa.probe = probe; sa.plan = plan; sa.n = n; sa.n_passes = kb;
@@ -365,32 +389,54 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     sa.hybrid = hybrid ? 1 : 0;
     sa.allow_reduce = (int)opt_allow_reduce.load();
     sa.margin_bits = (float)opt_margin_bits.load();
-    {
-      ProfScope ps(PK_SCAN, stream);
-      scan_kernel<<<1, RADIX, 0, stream>>>(sa);
-    }
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
+    sa.have_minmax = (int)ha.with_minmax;
+    sa.guess_p1 = ha.guess_p1; sa.ghist_exact = ghist_exact;
+    auto launch_scan = [&]() -> int {
+      {
+        ProfScope ps(PK_SCAN, stream);
+        scan_kernel<<<1, RADIX, 0, stream>>>(sa);
+      }
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    };
+    if (int rc = launch_scan()) return rc;
 
-    // Large hybrid sorts read the plan back (small D2H; the host waits on an event recorded right after
-    // it, while the histogram kernel below already runs) and launch only the passes that execute;
-    // otherwise every pass is launched and the skipped ones return at once.
+    // Large hybrid sorts read the plan back (small D2H, one host wait) and launch only what executes: the
+    // exact min/max sweep and a second planning step if asked for, the histogram kernel unless the probe's
+    // guess was right, the passes that are not skipped.  Smaller sorts launch everything; what is not
+    // needed returns at once.
     Plan hplan{};
     bool have_plan = false;
     static thread_local cudaEvent_t plan_event = nullptr;
-    if (hybrid && n >= (int64_t)1 << 24) {
+    HistArgs hb = ha;
+    hb.ghist = ghist_exact; hb.plan = plan; hb.probe = nullptr;
+    uint32_t hist_sweeps = 1;
+    if (big) {
       if (plan_event == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&plan_event, cudaEventDisableTiming));
       CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaEventRecord(plan_event, stream));
+      CUDA_TRY(cudaEventSynchronize(plan_event));
+      if (hplan.want_minmax) {
+        CUDA_TRY(launch_hist(kb, ha, di.sm_count, /*minmax=*/2, stream));
+        hist_sweeps++;
+        sa.have_minmax = 1;
+        if (int rc = launch_scan()) return rc;
+        CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaEventRecord(plan_event, stream));
+        CUDA_TRY(cudaEventSynchronize(plan_event));
+      }
       have_plan = true;
+      if (!hplan.hist_done) {
+        CUDA_TRY(launch_hist(kb, hb, di.sm_count, /*probe=*/0, stream));
+        hist_sweeps++;
+      }
+    } else {
+      // exact histogram of the first executed pass only; every pass counts its successor's digit
+      CUDA_TRY(launch_hist(kb, hb, di.sm_count, /*probe=*/0, stream));
+      hist_sweeps++;
     }
 
-    // exact histogram of the first executed pass only; every pass counts its successor's digit
-    HistArgs hb = ha;
-    hb.ghist = ghist_exact; hb.plan = plan; hb.probe = nullptr;
-    CUDA_TRY(launch_hist(kb, hb, di.sm_count, /*probe=*/false, stream));
-
-    if (have_plan) CUDA_TRY(cudaEventSynchronize(plan_event));
     const int64_t n_tiles = (n + tile - 1) / tile;
     HybridCtrl *ctrl = (HybridCtrl *)(ws + L.hyb_off);
     // With the plan on the host, an 8-byte-key SoA sort lets the LAST pass order the final segments each tile
@@ -469,7 +515,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       if (int rc = launch_copyback(false)) return rc;
     }
     stt.passes_planned = (uint32_t)kb;
-    stt.hist_sweeps = 2;  // probe + exact histogram of the first pass
+    stt.hist_sweeps = hist_sweeps;  // probe (+ exact min/max) (+ exact histogram of the first pass)
     stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
     if (hybrid) {
       // The plan was made on the device; read it (and the fall-back flag) back.  This is the one host
@@ -674,6 +720,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "hist_match")) return &opt_hist_match;
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
+  if (!strcmp(name, "probe_guess")) return &opt_probe_guess;
   if (!strcmp(name, "nstage")) return &opt_nstage;
   return nullptr;
 }

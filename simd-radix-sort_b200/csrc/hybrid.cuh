@@ -236,55 +236,103 @@ __device__ __forceinline__ void junction_permute(unsigned char *buf, int64_t lo,
   for (int x = 0; x < len; x++) d[(size_t)x * cpe] = tmp[src_of[x]];
 }
 
+template <typename T>
+__device__ __forceinline__ void junction_swap(unsigned char *buf, int64_t lo, uint32_t cpe, uint32_t c) {
+  T *d = reinterpret_cast<T *>(buf) + (size_t)lo * cpe + c;
+  const T x = d[0], y = d[cpe];
+  d[0] = y;
+  d[cpe] = x;
+}
+
 template <int KB>
 __global__ void __launch_bounds__(256) junction_fix_kernel(const __grid_constant__ JunctionArgs a) {
   using O = typename OrdOf<KB>::type;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t t = idx / RADIX;
-  const int d = (int)(idx % RADIX);
-  if (t >= a.n_tiles - 1) return;  // the last tile has no successor
-  const int64_t g = (int64_t)(a.lookback[(size_t)t * RADIX + d] & LB_VALUE_MASK);          // end of tile t's part
-  const int64_t g_end = (int64_t)(a.lookback[(size_t)(a.n_tiles - 1) * RADIX + d] & LB_VALUE_MASK);  // bucket end
-  if (g >= g_end) return;          // nothing of this bucket follows
-  const int64_t g_prev = t > 0 ? (int64_t)(a.lookback[(size_t)(t - 1) * RADIX + d] & LB_VALUE_MASK) : -1;
-  if (t > 0 && g == g_prev) return;  // tile t put nothing here: the junction coincides with an earlier one
-  if (g <= 0) return;
-
+  __shared__ int64_t q_g[256], q_prev[256];
+  __shared__ int q_n;
+  __shared__ uint32_t s_skip_all;
+  if (threadIdx.x == 0) { q_n = 0; s_skip_all = *reinterpret_cast<volatile uint32_t *>(a.flag); }
+  __syncthreads();
+  if (s_skip_all != 0) return;  // the full finish runs anyway (one decision per CTA: there are barriers below)
   const Stream &ks = a.ss.streams[0];
   const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
   unsigned char *kbuf = ks.buf[a.sel];
   const O pmask = (O)(~(O)0) << (8 * a.cut);
   auto okey = [&](int64_t i) -> O { return to_ordered<KB>(load_key<KB>(kbuf, i, key_stride), a.ko); };
-  const O k0 = okey(g - 1);
-  if (((k0 ^ okey(g)) & pmask) != 0) return;  // the common case: different segments on either side
-  int64_t lo = g - 1, hi = g + 1;
-  while (lo > 0 && g - lo <= JF_CAP && ((okey(lo - 1) ^ k0) & pmask) == 0) lo--;
-  while (hi < a.n && hi - g <= JF_CAP && ((okey(hi) ^ k0) & pmask) == 0) hi++;
-  const int len = (int)(hi - lo);
-  if (len > JF_CAP) { atomicOr(a.flag, 1u); return; }
-  if (t > 0 && lo < g_prev) return;  // an earlier junction lies inside this segment: its thread orders it
 
-  // rank counting on the full key -> source of every destination slot, then permute every stream
-  O keys[JF_CAP];
-  uint8_t src_of[JF_CAP];
-  for (int x = 0; x < len; x++) keys[x] = okey(lo + x);
-  bool moved = false;
-  for (int x = 0; x < len; x++) {
-    int r = 0;
-    for (int y = 0; y < len; y++) r += (keys[y] < keys[x] || (keys[y] == keys[x] && y < x)) ? 1 : 0;
-    src_of[r] = (uint8_t)x;
-    moved = moved || r != x;
+  // phase A, one thread per (tile, digit): do the two keys around the junction belong to one segment?
+  // (about one junction in ten for a plan that leaves 0.25 keys per segment: collected in shared memory so
+  // that the repair below runs with full warps instead of three lanes in 32)
+  {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = idx / RADIX;
+    const int d = (int)(idx % RADIX);
+    if (t < a.n_tiles - 1) {  // the last tile has no successor
+      const int64_t g = (int64_t)(a.lookback[(size_t)t * RADIX + d] & LB_VALUE_MASK);  // end of tile t's part
+      const int64_t g_end = (int64_t)(a.lookback[(size_t)(a.n_tiles - 1) * RADIX + d] & LB_VALUE_MASK);  // bucket end
+      const int64_t g_prev = t > 0 ? (int64_t)(a.lookback[(size_t)(t - 1) * RADIX + d] & LB_VALUE_MASK) : -1;
+      // g == g_prev: tile t put nothing here, the junction coincides with an earlier one
+      if (g < g_end && g > 0 && g != g_prev && ((okey(g - 1) ^ okey(g)) & pmask) == 0) {
+        const int slot = atomicAdd(&q_n, 1);
+        q_g[slot] = g;
+        q_prev[slot] = g_prev;
+      }
+    }
   }
-  if (!moved) return;
-  for (int s = 0; s < a.ss.n_streams; s++) {
-    const Stream &st = a.ss.streams[s];
-    for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
-      switch (st.chunk_bytes) {
-        case 1: junction_permute<uint8_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
-        case 2: junction_permute<uint16_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
-        case 4: junction_permute<uint32_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
-        case 8: junction_permute<uint64_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
-        default: junction_permute<uint4>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+  __syncthreads();
+
+  // phase B: order the segments found
+  const int n_q = q_n;
+  for (int qi = threadIdx.x; qi < n_q; qi += blockDim.x) {
+    const int64_t g = q_g[qi], g_prev = q_prev[qi];
+    const O k0 = okey(g - 1);
+    int64_t lo = g - 1, hi = g + 1;
+    while (lo > 0 && g - lo <= JF_CAP && ((okey(lo - 1) ^ k0) & pmask) == 0) lo--;
+    while (hi < a.n && hi - g <= JF_CAP && ((okey(hi) ^ k0) & pmask) == 0) hi++;
+    const int len = (int)(hi - lo);
+    if (len > JF_CAP) {  // too long to merge here: fine if the two parts happen to be in order (duplicates)
+      if (okey(g) < k0) atomicOr(a.flag, 1u);
+      continue;
+    }
+    if (lo < g_prev) continue;  // an earlier junction lies inside this segment: its thread orders it
+    if (len == 2) {  // by far the most common case
+      if (okey(g) < k0) {
+        for (int s = 0; s < a.ss.n_streams; s++) {
+          const Stream &st = a.ss.streams[s];
+          for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
+            switch (st.chunk_bytes) {
+              case 1: junction_swap<uint8_t>(st.buf[a.sel], lo, st.chunks_per_elem, c); break;
+              case 2: junction_swap<uint16_t>(st.buf[a.sel], lo, st.chunks_per_elem, c); break;
+              case 4: junction_swap<uint32_t>(st.buf[a.sel], lo, st.chunks_per_elem, c); break;
+              case 8: junction_swap<uint64_t>(st.buf[a.sel], lo, st.chunks_per_elem, c); break;
+              default: junction_swap<uint4>(st.buf[a.sel], lo, st.chunks_per_elem, c); break;
+            }
+          }
+        }
+      }
+      continue;
+    }
+    // rank counting on the full key -> source of every destination slot, then permute every stream
+    O keys[JF_CAP];
+    uint8_t src_of[JF_CAP];
+    for (int x = 0; x < len; x++) keys[x] = okey(lo + x);
+    bool moved = false;
+    for (int x = 0; x < len; x++) {
+      int r = 0;
+      for (int y = 0; y < len; y++) r += (keys[y] < keys[x] || (keys[y] == keys[x] && y < x)) ? 1 : 0;
+      src_of[r] = (uint8_t)x;
+      moved = moved || r != x;
+    }
+    if (!moved) continue;
+    for (int s = 0; s < a.ss.n_streams; s++) {
+      const Stream &st = a.ss.streams[s];
+      for (uint32_t c = 0; c < st.chunks_per_elem; c++) {
+        switch (st.chunk_bytes) {
+          case 1: junction_permute<uint8_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+          case 2: junction_permute<uint16_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+          case 4: junction_permute<uint32_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+          case 8: junction_permute<uint64_t>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+          default: junction_permute<uint4>(st.buf[a.sel], lo, len, src_of, st.chunks_per_elem, c); break;
+        }
       }
     }
   }

@@ -88,6 +88,8 @@ struct Plan {
   uint32_t next_exec_p1[MAX_PASSES];
   uint32_t skewed[MAX_PASSES];  // digit position has a low-entropy histogram: aggregate equal digits per warp
   unsigned long long sub;       // range reduction (KeyOrder::sub) chosen by the plan, 0 = none
+  uint32_t hist_done;           // probe_kernel's exact histogram (its guessed digit) is the first pass's: no hist_kernel
+  uint32_t want_minmax;         // a low-entropy digit: the smallest/largest key would tell whether range reduction pays
 };
 
 // per-sort scalars produced by probe_kernel (zero-initialised by the host)
@@ -96,6 +98,7 @@ struct ProbeOut {
   unsigned long long nand_bits;  // OR of the complements: a bit varies iff it is set in both words
   unsigned long long max_key;    // largest ordered key
   unsigned long long nmin_key;   // complement of the smallest ordered key (so that zero-initialisation works)
+  unsigned long long smax_key, snmin_key;  // the same over the sampled keys only (probe_kernel without with_minmax)
 };
 
 // look-back status word: [63:62] flag, [61:57] generation tag, [56:0] value
@@ -109,6 +112,11 @@ constexpr uint64_t LB_VALUE_MASK = (1ull << LB_TAG_SHIFT) - 1;
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
@@ -151,7 +159,11 @@ struct HistArgs {
   uint64_t *ghist;      // [KB][RADIX] counters, zeroed by the host
   const Plan *plan;     // hist_kernel: when set, count exactly the digit position plan->first_exec_p1 - 1
   ProbeOut *probe;      // probe_kernel
-  uint32_t sample;      // probe_kernel: every sample-th tile contributes to the histograms
+  uint32_t sample;      // probe_kernel: every sample-th tile contributes to the sampled histograms ...
+  uint32_t sample_one;  // ... with one key per thread (1) or all of its keys (0)
+  uint32_t with_minmax; // probe_kernel: also the smallest / largest key (else left to minmax_kernel, on demand)
+  uint32_t guess_p1;    // probe_kernel: digit position + 1 whose EXACT histogram is counted on the way (0 = none)
+  uint64_t *ghist_exact;  // [KB][RADIX] exact histograms (probe_kernel: row guess_p1 - 1)
 };
 
 // One digit of one key into the block's shared-memory counters.  Lanes of a warp that all hold the same
@@ -227,29 +239,68 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
   using KT = KeyTile<KB, THREADS, NLD>;
   using O = typename OrdOf<KB>::type;
   __shared__ uint32_t sh[KB * RADIX];
+  __shared__ uint32_t shx[RADIX];
   for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) sh[i] = 0;
+  for (int i = threadIdx.x; i < RADIX; i += THREADS) shx[i] = 0;
   __syncthreads();
   const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
+  const bool exact = a.guess_p1 != 0;
+  const int gshift = exact ? (int)(a.guess_p1 - 1) * RADIX_BITS : 0;
   O acc_or = 0, acc_nand = 0, acc_max = 0, acc_nmin = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
     kt.load(a.keys, a.stride, a.n, tile, a.ko);
+    if (a.with_minmax) {
 #pragma unroll
-    for (int i = 0; i < KT::PER_THREAD; i++)
-      if ((kt.valid >> i) & 1) {
-        acc_or |= kt.u[i];
-        acc_nand |= ~kt.u[i];
-        acc_max = kt.u[i] > acc_max ? kt.u[i] : acc_max;
-        acc_nmin = (O)~kt.u[i] > acc_nmin ? (O)~kt.u[i] : acc_nmin;
+      for (int i = 0; i < KT::PER_THREAD; i++)
+        if ((kt.valid >> i) & 1) {
+          acc_or |= kt.u[i];
+          acc_nand |= ~kt.u[i];
+          acc_max = kt.u[i] > acc_max ? kt.u[i] : acc_max;
+          acc_nmin = (O)~kt.u[i] > acc_nmin ? (O)~kt.u[i] : acc_nmin;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++)
+        if ((kt.valid >> i) & 1) {
+          acc_or |= kt.u[i];
+          acc_nand |= ~kt.u[i];
+        }
+    }
+    // the exact histogram of the digit position the first pass will most likely sweep (if the plan agrees,
+    // hist_kernel does not have to read the keys a second time)
+    if (exact) {
+      // plain shared-memory atomics unless this warp's first row shows a crowded digit (skewed keys would
+      // serialise on one counter): then equal digits are aggregated first
+      const uint32_t d0 = (uint32_t)(kt.u[0] >> gshift) & (RADIX - 1);
+      const bool full = kt.valid == (KT::PER_THREAD >= 32 ? 0xffffffffu : ((1u << KT::PER_THREAD) - 1));
+      const bool crowded = !__all_sync(0xffffffffu, full) ||
+                           __popc(__ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0))) >= 4;
+      if (crowded) {
+#pragma unroll
+        for (int i = 0; i < KT::PER_THREAD; i++) {
+          const bool v = (kt.valid >> i) & 1;
+          const unsigned vmask = __ballot_sync(0xffffffffu, v);
+          if (v) hist_add<true>(shx, (uint32_t)(kt.u[i] >> gshift) & (RADIX - 1), vmask);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < KT::PER_THREAD; i++) atomicAdd(&shx[(uint32_t)(kt.u[i] >> gshift) & (RADIX - 1)], 1u);
       }
+    }
     // every CTA samples every sample-th of ITS OWN tiles (tile % sample would pile all sampled tiles on
     // 1/sample of the CTAs when the grid size is a multiple of sample)
     if (((tile / gridDim.x) + blockIdx.x) % a.sample == 0) {
 #pragma unroll
       for (int i = 0; i < KT::PER_THREAD; i++) {
+        if (i > 0 && a.sample_one) break;
         const bool v = (kt.valid >> i) & 1;
         const unsigned vmask = __ballot_sync(0xffffffffu, v);
         if (v) {
+          if (!a.with_minmax) {  // range of the sample: tells the plan whether the exact range is worth a sweep
+            acc_max = kt.u[i] > acc_max ? kt.u[i] : acc_max;
+            acc_nmin = (O)~kt.u[i] > acc_nmin ? (O)~kt.u[i] : acc_nmin;
+          }
 #pragma unroll
           for (int p = 0; p < KB; p++)
             hist_add<USE_MATCH>(&sh[p * RADIX], (uint32_t)(kt.u[i] >> (p * RADIX_BITS)) & (RADIX - 1), vmask);
@@ -270,13 +321,56 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
   if ((threadIdx.x & 31) == 0) {
     atomicOr(&a.probe->or_bits, o);
     atomicOr(&a.probe->nand_bits, na);
-    atomicMax(&a.probe->max_key, mx);
-    atomicMax(&a.probe->nmin_key, nm);
+    if (a.with_minmax) {
+      atomicMax(&a.probe->max_key, mx);
+      atomicMax(&a.probe->nmin_key, nm);
+    } else {
+      atomicMax(&a.probe->smax_key, mx);
+      atomicMax(&a.probe->snmin_key, nm);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < KB * RADIX; i += THREADS) {
     const uint32_t c = sh[i];
     if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ghist[i]), (unsigned long long)c);
+  }
+  if (exact) {
+    uint64_t *out = a.ghist_exact + (size_t)(a.guess_p1 - 1) * RADIX;
+    for (int i = threadIdx.x; i < RADIX; i += THREADS) {
+      const uint32_t c = shx[i];
+      if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&out[i]), (unsigned long long)c);
+    }
+  }
+}
+
+// K1a': smallest and largest ordered key, only launched when the plan asks for them (Plan::want_minmax).
+template <int KB, int THREADS, int NLD>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) minmax_kernel(HistArgs a) {
+  using KT = KeyTile<KB, THREADS, NLD>;
+  using O = typename OrdOf<KB>::type;
+  const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
+  O acc_max = 0, acc_nmin = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    KT kt;
+    kt.load(a.keys, a.stride, a.n, tile, a.ko);
+#pragma unroll
+    for (int i = 0; i < KT::PER_THREAD; i++)
+      if ((kt.valid >> i) & 1) {
+        acc_max = kt.u[i] > acc_max ? kt.u[i] : acc_max;
+        acc_nmin = (O)~kt.u[i] > acc_nmin ? (O)~kt.u[i] : acc_nmin;
+      }
+  }
+  constexpr unsigned long long KEYMASK = KB == 8 ? ~0ull : ((1ull << (8 * (KB & 7))) - 1);
+  unsigned long long mx = acc_max, nm = acc_nmin & KEYMASK;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, s), n2 = __shfl_xor_sync(0xffffffffu, nm, s);
+    mx = m2 > mx ? m2 : mx;
+    nm = n2 > nm ? n2 : nm;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&a.probe->max_key, mx);
+    atomicMax(&a.probe->nmin_key, nm);
   }
 }
 
@@ -286,7 +380,7 @@ template <int KB, int THREADS, int NLD, bool USE_MATCH>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hist_kernel(HistArgs a) {
   using KT = KeyTile<KB, THREADS, NLD>;
   const uint32_t f = a.plan->first_exec_p1;
-  if (f == 0) return;  // nothing will be swept
+  if (f == 0 || a.plan->hist_done) return;  // nothing will be swept / probe_kernel counted this digit already
   const int shift = (int)(f - 1) * RADIX_BITS;
   const bool skewed = a.plan->skewed[f - 1] != 0;
   KeyOrder ko = a.ko;
@@ -334,6 +428,9 @@ struct ScanArgs {
   int hybrid;              // 1: choose cut_digit (MSB hybrid)
   int allow_reduce;        // 1: range reduction allowed
   float margin_bits;       // hybrid: sweep top digits until their entropies sum to log2(n) + margin_bits
+  int have_minmax;         // 1: probe->max_key / nmin_key are valid
+  uint32_t guess_p1;       // digit position + 1 probe_kernel counted exactly into ghist_exact (0 = none)
+  uint64_t *ghist_exact;
 };
 
 static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
@@ -341,6 +438,7 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
   __shared__ unsigned long long warp_tot[RADIX / 32];
   __shared__ uint32_t s_skip[MAX_PASSES];
   __shared__ float s_entropy[MAX_PASSES];
+  __shared__ uint32_t s_hist_done;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned long long varying = a.probe->or_bits & a.probe->nand_bits;  // bits on which keys differ
   if (t < MAX_PASSES) s_skip[t] = (a.allow_skip && t < a.n_passes && ((varying >> (t * RADIX_BITS)) & (RADIX - 1)) == 0) ? 1 : 0;
@@ -387,23 +485,35 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
     // Range reduction: if the keys span fewer digit positions than the plan above would sweep, subtract
     // the smallest key and sweep just those low digit positions (every digit above them is then zero).
     unsigned long long sub = 0;
+    uint32_t want_minmax = 0;
     {
       const unsigned long long kmask = a.n_passes >= 8 ? ~0ull : ((1ull << (8 * a.n_passes)) - 1);
-      const unsigned long long mn = (~a.probe->nmin_key) & kmask, mx = a.probe->max_key;
-      const unsigned long long range = mx - mn;
-      const int rb = range == 0 ? 0 : (63 - __clzll((long long)range)) / RADIX_BITS + 1;
       uint32_t planned = cut ? 1 : 0;  // the finish costs about a pass
       for (int p = 0; p < a.n_passes; p++) planned += s_skip[p] ? 0 : 1;
-      if (a.allow_reduce && mn != 0 && (uint32_t)rb < planned) {
-        sub = mn;
-        cut = 0;
-        for (int p = 0; p < a.n_passes; p++) {
-          s_skip[p] = p >= rb ? 1 : 0;
-          s_entropy[p] = 0.f;  // unknown for the shifted keys: treat every digit as skewed (safe)
+      auto digits_of_range = [&](unsigned long long mn, unsigned long long mx) -> int {
+        const unsigned long long range = mx - mn;
+        return range == 0 ? 0 : (63 - __clzll((long long)range)) / RADIX_BITS + 1;
+      };
+      if (!a.have_minmax) {
+        // only the range of the sampled keys is known: if even that spans as many digit positions as the plan
+        // sweeps, the true range cannot do better; else it is worth one more read of the keys (minmax_kernel)
+        const unsigned long long mn = (~a.probe->snmin_key) & kmask, mx = a.probe->smax_key;
+        if (a.allow_reduce && mn != 0 && mx >= mn && (uint32_t)digits_of_range(mn, mx) < planned) want_minmax = 1;
+      } else {
+        const unsigned long long mn = (~a.probe->nmin_key) & kmask, mx = a.probe->max_key;
+        const int rb = digits_of_range(mn, mx);
+        if (a.allow_reduce && mn != 0 && (uint32_t)rb < planned) {
+          sub = mn;
+          cut = 0;
+          for (int p = 0; p < a.n_passes; p++) {
+            s_skip[p] = p >= rb ? 1 : 0;
+            s_entropy[p] = 0.f;  // unknown for the shifted keys: treat every digit as skewed (safe)
+          }
         }
       }
     }
     a.plan->sub = sub;
+    a.plan->want_minmax = want_minmax;
     uint32_t sel = 0, n_exec = 0;
     int prev = -1;
     a.plan->first_exec_p1 = 0;
@@ -423,7 +533,12 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
     a.plan->n_exec = n_exec;
     a.plan->cut_digit = cut;
     a.plan->n_const = n_const;
+    s_hist_done = (a.guess_p1 != 0 && a.plan->first_exec_p1 == a.guess_p1 && sub == 0) ? 1u : 0u;
+    a.plan->hist_done = s_hist_done;
   }
+  __syncthreads();
+  // a wrong guess: that row of the exact histograms has to be empty again before a pass counts into it
+  if (a.guess_p1 != 0 && !s_hist_done) a.ghist_exact[(size_t)(a.guess_p1 - 1) * RADIX + t] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,7 +579,7 @@ struct SweepArgs {
   uint32_t *fix_flag;
 };
 
-constexpr int FIX_CAP = 16;  // longest run of keys agreeing on all swept bits that is ordered on the fly
+constexpr int FIX_CAP = 8;   // longest run of keys agreeing on all swept bits that is ordered on the fly
 
 // Per-pass constants that make the digit a handful of 32-bit operations: because the order mapping is
 // an xor, digit(ordered key) = digit(raw key) ^ digit(xor_const) ^ (negative ? digit(neg_xor) : 0).
@@ -813,6 +928,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     gbase[tid] = (int64_t)excl - (int64_t)s_prefix[tid];
   }
   if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
+  __shared__ uint32_t s_given_up;
+  if (FIX && tid == 0) s_given_up = ld_relaxed_u32(a.fix_flag);  // one decision for the whole tile (see below)
   __syncthreads();  // column 0, sdigit and gbase visible to everyone
 
   if constexpr (FIX) {
@@ -836,66 +953,69 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       // threads' windows are IPT keys apart.  (Equal swept bits of the ordered keys <=> equal swept bits of
       // the raw keys: the order mapping is an xor whose only key-dependent part is the sign bit, itself a
       // swept bit, and no range reduction is active when a cut exists.  Sentinel 1 never equals a masked key.)
-      constexpr int W = IPT + 2;
-      const int rot = lane % W;
-      uint32_t eq = 0;  // bit k: window positions (k+rot)%W and (k+1+rot)%W hold equal swept bits
-      auto scan_window = [&](auto tag) {
-        using T = decltype(tag);
-        T pref[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-          int w = k + rot;
-          if (w >= W) w -= W;
-          const int i = base - 1 + w;
-          T v = (T)1;
-          if (i >= 0 && i < lim) {
-            if constexpr (sizeof(T) == sizeof(O)) v = (T)((O)kst[i] & pmask);
-            else v = reinterpret_cast<const uint32_t *>(kst)[2 * i + 1] & (uint32_t)((uint64_t)pmask >> 32);
+      // once any tile has met a run that is too long, the full segment finish is going to run anyway: the
+      // tiles after it do not bother (keys with many duplicates would otherwise pay for nothing).  The whole
+      // tile takes the same decision: the members of a run must all apply their displacement, or none.
+      if (s_given_up == 0) {
+        constexpr int W = IPT + 2;
+        const int rot = lane % W;
+        uint32_t eq = 0;  // bit k: window positions (k+rot)%W and (k+1+rot)%W hold equal swept bits
+        auto scan_window = [&](auto tag) {
+          using T = decltype(tag);
+          T pref[W];
+  #pragma unroll
+          for (int k = 0; k < W; k++) {
+            int w = k + rot;
+            if (w >= W) w -= W;
+            const int i = base - 1 + w;
+            T v = (T)1;
+            if (i >= 0 && i < lim) {
+              if constexpr (sizeof(T) == sizeof(O)) v = (T)((O)kst[i] & pmask);
+              else v = reinterpret_cast<const uint32_t *>(kst)[2 * i + 1] & (uint32_t)((uint64_t)pmask >> 32);
+            }
+            pref[k] = v;
           }
-          pref[k] = v;
-        }
-#pragma unroll
-        for (int k = 0; k < W; k++) eq |= (uint32_t)(pref[k] == pref[(k + 1) % W]) << k;
-      };
-      if (KB == 8 && a.fix_cut >= 4) scan_window((uint32_t)0); else scan_window((O)0);
-      // re-index by window position: bit j = slots (base-1+j, base+j) agree, j = 0 .. IPT; bit W-1 is the wrap
-      eq = ((eq << rot) | (eq >> (W - rot))) & ((1u << (W - 1)) - 1u);
-      uint32_t members = (eq | (eq >> 1)) & ((1u << IPT) - 1u);  // own slots with an equal neighbour
-      if (!FULL) members &= lim - base >= IPT ? ~0u : (1u << max(lim - base, 0)) - 1u;  // sentinels are no members
-      while (members) {
-        const int sl = __ffs(members) - 1;
-        members &= members - 1;
-        const int i = base + sl;
-        const KeyT kraw = kst[i];
-        const O ok = to_ordered<KB>(kraw, ko);
-        // neighbours known to be in the run from the window bits, then (rarely) beyond the window
-        const uint32_t below = ~eq & ((2u << sl) - 1u);  // zero bits at or below sl stop the run on the left
-        int nl = below ? sl - (31 - __clz(below)) : sl + 1;
-        const uint32_t above = ~(eq >> (sl + 1));
-        int nr = __ffs(above) - 1;  // IPT - sl when the run reaches the end of the window
-        int cl = 0, cr = 0;
-        for (int q = 1; q <= nl; q++) cl += to_ordered<KB>(kst[i - q], ko) > ok;
-        for (int q = 1; q <= nr; q++) cr += to_ordered<KB>(kst[i + q], ko) < ok;
-        bool over = false;
-        if (nl == sl + 1) {  // the run includes slot base-1: it may go on further left
-          int j = i - nl - 1;
-          while (j >= 0 && (((O)kst[j] ^ (O)kraw) & pmask) == 0) {
-            if (++nl > FIX_CAP) { over = true; break; }
-            cl += to_ordered<KB>(kst[j], ko) > ok;
-            j--;
+  #pragma unroll
+          for (int k = 0; k < W; k++) eq |= (uint32_t)(pref[k] == pref[(k + 1) % W]) << k;
+        };
+        if (KB == 8 && a.fix_cut >= 4) scan_window((uint32_t)0); else scan_window((O)0);
+        // re-index by window position: bit j = slots (base-1+j, base+j) agree, j = 0 .. IPT; bit W-1 is the wrap
+        eq = ((eq << rot) | (eq >> (W - rot))) & ((1u << (W - 1)) - 1u);
+        uint32_t members = (eq | (eq >> 1)) & ((1u << IPT) - 1u);  // own slots with an equal neighbour
+        if (!FULL) members &= lim - base >= IPT ? ~0u : (1u << max(lim - base, 0)) - 1u;  // sentinels are no members
+        while (members) {
+          const int sl = __ffs(members) - 1;
+          members &= members - 1;
+          const int i = base + sl;
+          const KeyT kraw = kst[i];
+          const O ok = to_ordered<KB>(kraw, ko);
+          // neighbours known to be in the run from the window bits, then (rarely) beyond the window
+          const uint32_t below = ~eq & ((2u << sl) - 1u);  // zero bits at or below sl stop the run on the left
+          int nl = below ? sl - (31 - __clz(below)) : sl + 1;
+          const uint32_t above = ~(eq >> (sl + 1));
+          int nr = __ffs(above) - 1;  // IPT - sl when the run reaches the end of the window
+          // extent of the run: beyond the window only if it reaches the window's ends, and never further than
+          // it takes to know that it is too long (nl + nr = run length - 1 for every member alike)
+          if (nl == sl + 1 && nl + nr <= FIX_CAP) {  // includes slot base-1
+            int j = i - nl - 1;
+            while (j >= 0 && nl + nr <= FIX_CAP && (((O)kst[j] ^ (O)kraw) & pmask) == 0) { nl++; j--; }
           }
-        }
-        if (nr == IPT - sl) {  // includes slot base+IPT
-          int j = i + nr + 1;
-          while (j < lim && (((O)kst[j] ^ (O)kraw) & pmask) == 0) {
-            if (++nr > FIX_CAP) { over = true; break; }
-            cr += to_ordered<KB>(kst[j], ko) < ok;
-            j++;
+          if (nr == IPT - sl && nl + nr <= FIX_CAP) {  // includes slot base+IPT
+            int j = i + nr + 1;
+            while (j < lim && nl + nr <= FIX_CAP && (((O)kst[j] ^ (O)kraw) & pmask) == 0) { nr++; j++; }
           }
+          int cl = 0, cr = 0;
+          if (nl + nr > FIX_CAP) {
+            // Too long to be ordered here: every member keeps its slot and checks its own (slot, slot+1) pair;
+            // if none is out of order the run is in order as it stands (duplicates of one key, typically)
+            // and nobody has to be told.
+            if (((eq >> (sl + 1)) & 1u) && to_ordered<KB>(kst[i + 1], ko) < ok && ld_relaxed_u32(a.fix_flag) == 0) atomicOr(a.fix_flag, 1u);
+          } else {
+            for (int q = 1; q <= nl; q++) cl += to_ordered<KB>(kst[i - q], ko) > ok;
+            for (int q = 1; q <= nr; q++) cr += to_ordered<KB>(kst[i + q], ko) < ok;
+          }
+          if (cr != cl) sdelta[i] = (int8_t)(cr - cl);
         }
-        // every member sees the same total length unless it hit the cap, so all of them agree on "too long"
-        if (over || nl + nr > FIX_CAP) atomicOr(a.fix_flag, 1u);
-        else if (cr != cl) sdelta[i] = (int8_t)(cr - cl);
       }
       __syncthreads();
     }
