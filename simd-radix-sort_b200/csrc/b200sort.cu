@@ -43,6 +43,8 @@ static std::atomic<int64_t> opt_fix_in_pass{1};  // order tile-local segments in
 static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 static std::atomic<int64_t> opt_probe_guess{1};
+static std::atomic<int64_t> opt_allow_lshift{1};
+static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at least 2^this records read the plan back
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
 enum ProfKind { PK_HIST = 0, PK_SCAN = 1, PK_SWEEP = 2, PK_COPYBACK = 3, PK_SEGFIX = 4, PK_OTHER = 5 };
@@ -101,7 +103,7 @@ KeyOrder make_key_order(int key_type, bool ascending) {
   const bool is_signed = key_type == B200SORT_I8 || key_type == B200SORT_I16 || key_type == B200SORT_I32 ||
                          key_type == B200SORT_I64;
   const bool is_float = key_type == B200SORT_F32 || key_type == B200SORT_F64;
-  KeyOrder ko{0, 0, 0};
+  KeyOrder ko{0, 0, 0, 0, 0};
   if (is_signed || is_float) ko.xor_const = sign;
   if (is_float) ko.neg_xor = mask ^ sign;
   if (!ascending) ko.xor_const ^= mask;
@@ -115,7 +117,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false) {
   const size_t tile = (size_t)c.threads * c.ipt;
-  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 + RADIX * 4 +
+  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 +
          (fix ? tile : 0);  // FIX: per-slot displacement
 }
 
@@ -357,7 +359,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     ha.keys = ss.streams[0].buf[0];
     ha.stride = streams[0].elem_bytes;
     ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
-    const bool big = hybrid && n >= (int64_t)1 << 24;  // the host reads the plan back
+    const bool big = hybrid && n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);  // the host reads the plan back
     {
       const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
       // entropies from one key per thread of every 8th tile once there are plenty of tiles
@@ -390,6 +392,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     sa.allow_reduce = (int)opt_allow_reduce.load();
     sa.margin_bits = (float)opt_margin_bits.load();
     sa.have_minmax = (int)ha.with_minmax;
+    sa.allow_lshift = (int)opt_allow_lshift.load();
     sa.guess_p1 = ha.guess_p1; sa.ghist_exact = ghist_exact;
     auto launch_scan = [&]() -> int {
       {
@@ -443,7 +446,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     // holds and repairs the tile-straddling ones with junction_fix_kernel; the full segment finish then only
     // runs if one of them reports a run that is too long.
     const bool soa = streams[0].elem_bytes == (uint32_t)kb;
-    const bool use_fix = have_plan && hplan.cut_digit != 0 && soa && cfg == 1 && opt_fix_in_pass.load() != 0;
+    const bool use_fix = have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == 1 && opt_fix_in_pass.load() != 0;
     int last_pass = -1;
     for (int p = 0; p < kb; p++) {
       if (have_plan && hplan.skip[p]) continue;
@@ -454,7 +457,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes; wa.spin_ns = (uint32_t)opt_spin_ns.load();
       if (have_plan) {
         wa.plan_in_args = 1; wa.arg_sel = hplan.src_sel[p]; wa.arg_next_p1 = hplan.next_exec_p1[p];
-        wa.arg_next_skewed = hplan.next_exec_p1[p] ? hplan.skewed[hplan.next_exec_p1[p] - 1] : 0; wa.arg_sub = hplan.sub;
+        wa.arg_next_skewed = hplan.next_exec_p1[p] ? hplan.skewed[hplan.next_exec_p1[p] - 1] : 0; wa.arg_sub = hplan.sub; wa.arg_lshift = hplan.lshift;
         if (use_fix && hplan.next_exec_p1[p] == 0) { wa.fix_cut = hplan.cut_digit; wa.fix_flag = &ctrl->flags[1]; last_pass = p; }
       }
       CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream));
@@ -462,7 +465,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     auto launch_segfix = [&]() -> int {
       SegfixArgs fa{};
       fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl;
-      if (have_plan) { fa.plan_in_args = 1; fa.arg_cut = hplan.cut_digit; fa.arg_sel = hplan.final_sel; fa.arg_sub = hplan.sub; }
+      if (have_plan) { fa.plan_in_args = 1; fa.arg_cut = hplan.cut_digit; fa.arg_sel = hplan.final_sel; fa.arg_sub = hplan.sub; fa.arg_lshift = hplan.lshift; }
       bool any = false;
       for (int s = 0; s < ss.n_streams; s++) any = any || ss.streams[s].chunk_bytes < 4;
       const unsigned grid = (unsigned)std::min<int64_t>((n + SF_FT - 1) / SF_FT, (int64_t)di.sm_count * 16);
@@ -489,7 +492,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     bool finish_ran = false;
     if (last_pass >= 0) {
       JunctionArgs ja{};
-      ja.ss = ss; ja.n = n; ja.ko = ko; ja.ko.sub = hplan.sub; ja.lookback = lookback; ja.n_tiles = n_tiles;
+      ja.ss = ss; ja.n = n; ja.ko = ko; ja.ko.sub = hplan.sub; ja.ko.lshift = hplan.lshift; ja.lookback = lookback; ja.n_tiles = n_tiles;
       ja.tag = (uint32_t)(last_pass + 1); ja.cut = hplan.cut_digit; ja.sel = hplan.final_sel; ja.flag = &ctrl->flags[1];
       const int64_t threads = n_tiles * RADIX;
       {
@@ -721,6 +724,8 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
   if (!strcmp(name, "probe_guess")) return &opt_probe_guess;
+  if (!strcmp(name, "allow_lshift")) return &opt_allow_lshift;
+  if (!strcmp(name, "host_plan_min_log2")) return &opt_host_plan_min_log2;
   if (!strcmp(name, "nstage")) return &opt_nstage;
   return nullptr;
 }

@@ -42,6 +42,7 @@ struct SegfixArgs {
   // plan values as arguments when the host has read the plan back (no dependent load at CTA start)
   uint32_t plan_in_args, arg_cut, arg_sel;
   unsigned long long arg_sub;
+  uint32_t arg_lshift;
 };
 
 // Moves the queued elements of one chunk column (one warp): entry i goes from window position q_p[i] to
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
   const unsigned char *ksrc = ks.buf[sel];
   KeyOrder ko = a.ko;
   ko.sub = a.plan_in_args ? a.arg_sub : a.plan->sub;
+  ko.lshift = a.plan_in_args ? a.arg_lshift : a.plan->lshift;
 
   O key[SF_PPT];
 #pragma unroll

@@ -40,14 +40,17 @@ struct KeyOrder {
   uint64_t sub;        // range reduction: the smallest mapped key of this sort (or 0), subtracted last.
                        // Keys of a narrow range that straddles the sign (e.g. -8..7, N(0,100)) differ in every
                        // digit position; after the subtraction only the low digit positions vary.
+  uint32_t lshift;     // left shift applied last (0..7): when the keys agree on their leading l bits, the digit
+  uint32_t pad_;       // positions of the shifted key are windows of the key that start right below them
 };
 
-template <int KB>
+template <int KB, bool SHIFT = true>
 __device__ __forceinline__ typename OrdOf<KB>::type to_ordered(typename UIntOf<KB>::type raw, const KeyOrder &ko) {
   using O = typename OrdOf<KB>::type;
   O u = (O)raw;
   const O neg = (O)0 - ((u >> (8 * KB - 1)) & 1);  // all ones when the sign bit is set
-  return (u ^ (O)ko.xor_const ^ (neg & (O)ko.neg_xor)) - (O)ko.sub;
+  const O v = (u ^ (O)ko.xor_const ^ (neg & (O)ko.neg_xor)) - (O)ko.sub;
+  return SHIFT ? (O)(v << ko.lshift) : v;  // SHIFT = false: callers that know lshift == 0 (the probe)
 }
 
 template <int KB>
@@ -88,6 +91,7 @@ struct Plan {
   uint32_t next_exec_p1[MAX_PASSES];
   uint32_t skewed[MAX_PASSES];  // digit position has a low-entropy histogram: aggregate equal digits per warp
   unsigned long long sub;       // range reduction (KeyOrder::sub) chosen by the plan, 0 = none
+  uint32_t lshift;              // KeyOrder::lshift chosen by the plan, 0 = none
   uint32_t hist_done;           // probe_kernel's exact histogram (its guessed digit) is the first pass's: no hist_kernel
   uint32_t want_minmax;         // a low-entropy digit: the smallest/largest key would tell whether range reduction pays
 };
@@ -198,6 +202,7 @@ struct KeyTile {
   O u[PER_THREAD];
   uint32_t valid;  // bit i: u[i] holds a key
 
+  template <bool SHIFT = true>
   __device__ __forceinline__ void load(const unsigned char *keys, uint32_t stride, int64_t n, int64_t tile, const KeyOrder &ko) {
     using KeyT = typename UIntOf<KB>::type;
     const int64_t base = tile * TILE;
@@ -213,7 +218,7 @@ struct KeyTile {
         KeyT k[VEC];
         memcpy(k, &q[j], 16);
 #pragma unroll
-        for (int e = 0; e < VEC; e++) u[j * VEC + e] = to_ordered<KB>(k[e], ko);
+        for (int e = 0; e < VEC; e++) u[j * VEC + e] = to_ordered<KB, SHIFT>(k[e], ko);
       }
       valid = PER_THREAD >= 32 ? 0xffffffffu : ((1u << PER_THREAD) - 1);
     } else {
@@ -221,7 +226,7 @@ struct KeyTile {
       for (int i = 0; i < PER_THREAD; i++) {
         const int64_t idx = base + (int64_t)i * THREADS + threadIdx.x;
         if (idx < n) {
-          u[i] = to_ordered<KB>(load_key<KB>(keys, idx, stride), ko);
+          u[i] = to_ordered<KB, SHIFT>(load_key<KB>(keys, idx, stride), ko);
           valid |= 1u << i;
         } else {
           u[i] = 0;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
   O acc_or = 0, acc_nand = 0, acc_max = 0, acc_nmin = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
-    kt.load(a.keys, a.stride, a.n, tile, a.ko);
+    kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);
     if (a.with_minmax) {
 #pragma unroll
       for (int i = 0; i < KT::PER_THREAD; i++)
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) minmax_kernel(HistArg
   O acc_max = 0, acc_nmin = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
-    kt.load(a.keys, a.stride, a.n, tile, a.ko);
+    kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);
 #pragma unroll
     for (int i = 0; i < KT::PER_THREAD; i++)
       if ((kt.valid >> i) & 1) {
@@ -385,6 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hist_kernel(HistArgs 
   const bool skewed = a.plan->skewed[f - 1] != 0;
   KeyOrder ko = a.ko;
   ko.sub = a.plan->sub;
+  ko.lshift = a.plan->lshift;
   __shared__ uint32_t sh[RADIX];
   for (int i = threadIdx.x; i < RADIX; i += THREADS) sh[i] = 0;
   __syncthreads();
@@ -429,6 +435,7 @@ struct ScanArgs {
   int allow_reduce;        // 1: range reduction allowed
   float margin_bits;       // hybrid: sweep top digits until their entropies sum to log2(n) + margin_bits
   int have_minmax;         // 1: probe->max_key / nmin_key are valid
+  int allow_lshift;        // 1: the plan may shift the keys left by their common leading bits
   uint32_t guess_p1;       // digit position + 1 probe_kernel counted exactly into ghist_exact (0 = none)
   uint64_t *ghist_exact;
 };
@@ -466,21 +473,59 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
   if (t == 0) {
     uint32_t cut = 0, n_const = 0;
     for (int p = 0; p < a.n_passes; p++) n_const += s_skip[p];
+    uint32_t lshift = 0;
     if (a.hybrid) {
       // MSB hybrid: sweep only the top digits whose (marginal) entropies add up to log2(n) + margin; the
       // runs that still agree on those digits are then short (expected length 2^-margin) or constant, and
-      // segfix_kernel finishes them in shared memory.  A cut that saves fewer than two sweeps is not
-      // worth the finishing pass.
-      float acc = 0.f;
+      // the finish orders them.  A cut that saves fewer than two sweeps is not worth the finishing pass.
       const float need = log2f((float)a.n) + a.margin_bits;
-      for (int p = a.n_passes - 1; p >= 0; p--) {
-        if (!s_skip[p]) acc += s_entropy[p];
-        if (acc >= need) { cut = (uint32_t)p; break; }
+      auto choose_cut = [&](const float *ent, uint32_t *skip, uint32_t *n_exec) -> uint32_t {
+        uint32_t c = 0;
+        float acc = 0.f;
+        for (int p = a.n_passes - 1; p >= 0; p--) {
+          if (!skip[p]) acc += ent[p];
+          if (acc >= need) { c = (uint32_t)p; break; }
+        }
+        uint32_t saved = 0;
+        for (uint32_t p = 0; p < c; p++) saved += skip[p] ? 0 : 1;
+        if (saved < 2) c = 0;
+        for (uint32_t p = 0; p < c; p++) skip[p] = 1;
+        *n_exec = 0;
+        for (int p = 0; p < a.n_passes; p++) *n_exec += skip[p] ? 0 : 1;
+        return c;
+      };
+      // Variant with the keys shifted left by the l (< 8) leading bits on which they all agree: the digit
+      // positions then start right below those bits, and the top position is a full 8-bit digit instead of
+      // 8-l varying bits (a shard of a multi-GPU sort has its leading bits fixed by the partition).  The
+      // entropies of the shifted positions are estimated from those measured on the unshifted ones, a
+      // position's entropy taken as evenly spread over its varying bits.
+      uint32_t skip2[MAX_PASSES];
+      float ent2[MAX_PASSES];
+      const int l = (a.allow_lshift && a.n_passes == 8 && varying != 0) ? (__clzll((long long)varying) & 7) : 0;
+      if (l != 0) {
+        const unsigned long long varying2 = varying << l;
+        for (int p = 0; p < a.n_passes; p++) {
+          const uint32_t vb = (uint32_t)(varying >> (p * RADIX_BITS)) & (RADIX - 1);
+          const uint32_t vb_lo = p > 0 ? (uint32_t)(varying >> ((p - 1) * RADIX_BITS)) & (RADIX - 1) : 0u;
+          const int n_all = __popc(vb), n_take = __popc(vb & (0xffu >> l));            // this position's low 8-l bits
+          const int m_all = __popc(vb_lo), m_take = __popc(vb_lo & ~(0xffu >> l) & 0xffu);  // top l bits of the one below
+          float e = 0.f;
+          if (n_all) e += s_entropy[p] * (float)n_take / (float)n_all;
+          if (m_all) e += s_entropy[p - 1] * (float)m_take / (float)m_all;
+          ent2[p] = e;
+          skip2[p] = (a.allow_skip && ((varying2 >> (p * RADIX_BITS)) & (RADIX - 1)) == 0) ? 1u : 0u;
+        }
       }
-      uint32_t saved = 0;
-      for (uint32_t p = 0; p < cut; p++) saved += s_skip[p] ? 0 : 1;
-      if (saved < 2) cut = 0;
-      for (uint32_t p = 0; p < cut; p++) s_skip[p] = 1;
+      uint32_t n1 = 0, n2 = 0;
+      cut = choose_cut(s_entropy, s_skip, &n1);
+      if (l != 0) {
+        const uint32_t cut2 = choose_cut(ent2, skip2, &n2);
+        if (cut2 != 0 && n2 < n1) {
+          lshift = (uint32_t)l;
+          cut = cut2;
+          for (int p = 0; p < a.n_passes; p++) { s_skip[p] = skip2[p]; s_entropy[p] = ent2[p]; }
+        }
+      }
     }
     // Range reduction: if the keys span fewer digit positions than the plan above would sweep, subtract
     // the smallest key and sweep just those low digit positions (every digit above them is then zero).
@@ -505,6 +550,7 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
         if (a.allow_reduce && mn != 0 && (uint32_t)rb < planned) {
           sub = mn;
           cut = 0;
+          lshift = 0;
           for (int p = 0; p < a.n_passes; p++) {
             s_skip[p] = p >= rb ? 1 : 0;
             s_entropy[p] = 0.f;  // unknown for the shifted keys: treat every digit as skewed (safe)
@@ -513,6 +559,7 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
       }
     }
     a.plan->sub = sub;
+    a.plan->lshift = lshift;
     a.plan->want_minmax = want_minmax;
     uint32_t sel = 0, n_exec = 0;
     int prev = -1;
@@ -533,7 +580,7 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
     a.plan->n_exec = n_exec;
     a.plan->cut_digit = cut;
     a.plan->n_const = n_const;
-    s_hist_done = (a.guess_p1 != 0 && a.plan->first_exec_p1 == a.guess_p1 && sub == 0) ? 1u : 0u;
+    s_hist_done = (a.guess_p1 != 0 && a.plan->first_exec_p1 == a.guess_p1 && sub == 0 && lshift == 0) ? 1u : 0u;
     a.plan->hist_done = s_hist_done;
   }
   __syncthreads();
@@ -573,6 +620,7 @@ struct SweepArgs {
   // CTA does not start with a dependent global load (244 K CTAs per pass at 1e9 records).
   uint32_t plan_in_args, arg_sel, arg_next_p1, arg_next_skewed;
   unsigned long long arg_sub;
+  uint32_t arg_lshift;
   // FIX instantiation (last pass of the MSB hybrid plan): Plan::cut_digit and where to report a run of
   // more than FIX_CAP keys that agree on all swept bits (the full segment finish then has to run)
   uint32_t fix_cut;
@@ -589,12 +637,15 @@ struct DigitX {
   uint32_t xc, nx;   // digit(xor_const), digit(neg_xor)
 };
 
+// (a left shift of the ordered key by l bits moves the digit at `shift` to bit shift - l of the unshifted key;
+//  it may then straddle the two 32-bit words: the funnel shift takes care of that)
 __device__ __forceinline__ DigitX make_digitx(const KeyOrder &ko, int shift) {
   DigitX x;
-  x.hi_word = shift >= 32;
-  x.bit = shift & 31;
-  x.xc = (uint32_t)(ko.xor_const >> shift) & (RADIX - 1);
-  x.nx = (uint32_t)(ko.neg_xor >> shift) & (RADIX - 1);
+  const int es = shift - (int)ko.lshift;  // callers use this path only when es >= 0
+  x.hi_word = es >= 32;
+  x.bit = es & 31;
+  x.xc = (uint32_t)(ko.xor_const >> es) & (RADIX - 1);
+  x.nx = (uint32_t)(ko.neg_xor >> es) & (RADIX - 1);
   return x;
 }
 
@@ -602,9 +653,9 @@ template <int KB>
 __device__ __forceinline__ uint32_t fast_digit(typename UIntOf<KB>::type raw, const DigitX &x) {
   if constexpr (KB == 8) {
     const uint32_t hi = (uint32_t)(raw >> 32), lo = (uint32_t)raw;
-    const uint32_t w = x.hi_word ? hi : lo;
+    const uint32_t w = x.hi_word ? (hi >> x.bit) : __funnelshift_r(lo, hi, x.bit);
     const uint32_t neg = (uint32_t)((int32_t)hi >> 31);
-    return (((w >> x.bit) & (RADIX - 1)) ^ x.xc) ^ (neg & x.nx);
+    return ((w & (RADIX - 1)) ^ x.xc) ^ (neg & x.nx);
   } else {
     const uint32_t w = (uint32_t)raw;
     const uint32_t neg = (uint32_t)((int32_t)(w << (32 - 8 * KB)) >> 31);
@@ -692,8 +743,9 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   uint32_t *s_wsum = s_prefix + RADIX;                                                        // 32
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
   uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
-  uint32_t *nhist = reinterpret_cast<uint32_t *>(sdigit + TILE);                             // RADIX (zeroed by the kernel)
-  int8_t *sdelta = reinterpret_cast<int8_t *>(nhist + RADIX);                                // TILE (FIX only): slot displacement
+  uint32_t *nhist = s_prefix;  // RADIX, zeroed by the kernel: the next digit's counts live here until thread d has
+                               // read nhist[d], just before it writes s_prefix[d]
+  int8_t *sdelta = reinterpret_cast<int8_t *>(sdigit + TILE);                                // TILE (FIX only): slot displacement
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile_base = tile * TILE;
@@ -711,7 +763,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   // Digits are computed once and kept packed four to a register (IPT/4 registers).
   KeyOrder ko = a.ko;
   ko.sub = LUT ? 0ull : (a.plan_in_args ? a.arg_sub : a.plan->sub);
-  const bool has_sub = ko.sub != 0;  // range reduction active: the xor shortcut of fast_digit does not apply
+  ko.lshift = LUT ? 0u : (a.plan_in_args ? a.arg_lshift : a.plan->lshift);
+  // range reduction active (or a shift larger than this digit's offset, which the plan never produces): the
+  // xor shortcut of fast_digit does not apply
+  const bool has_sub = ko.sub != 0 || (int)ko.lshift > a.shift;
   static_assert(IPT % 4 == 0, "digits are packed four per register");
   uint32_t dpack[IPT / 4];
   {
@@ -940,10 +995,15 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     // belongs inside the run and leaves the displacement in sdelta[slot]; the destination offsets of ALL
     // columns (goff, below) pick it up.  Only segments that straddle two tiles are left for
     // junction_fix_kernel.
-    if (soa_keys) {
+    {
       using O = typename OrdOf<KB>::type;
-      const KeyT *kst = reinterpret_cast<const KeyT *>(bufs[0]);
-      const O pmask = (O)(~(O)0) << (8 * a.fix_cut);
+      // column 0 holds the keys: the key array itself, or the leading chunk of every record (key at offset 0)
+      const KeyT *kcol = reinterpret_cast<const KeyT *>(bufs[0]);
+      const int kstep = soa_keys ? 1 : (int)(ks.chunk_bytes / KB);
+      auto key_at = [&](int i) -> KeyT { return kcol[i * kstep]; };
+      // swept bits of the ordered (and possibly left-shifted) key, as a mask on the raw key
+      const int cut_bit = 8 * (int)a.fix_cut - (int)ko.lshift;
+      const O pmask = (O)(~(O)0) << cut_bit;
       const int base = tid * IPT;
       const int lim = FULL ? TILE : n_valid;
 #pragma unroll
@@ -970,15 +1030,15 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
             const int i = base - 1 + w;
             T v = (T)1;
             if (i >= 0 && i < lim) {
-              if constexpr (sizeof(T) == sizeof(O)) v = (T)((O)kst[i] & pmask);
-              else v = reinterpret_cast<const uint32_t *>(kst)[2 * i + 1] & (uint32_t)((uint64_t)pmask >> 32);
+              if constexpr (sizeof(T) == sizeof(O)) v = (T)((O)key_at(i) & pmask);
+              else v = reinterpret_cast<const uint32_t *>(kcol)[2 * i * kstep + 1] & (uint32_t)((uint64_t)pmask >> 32);
             }
             pref[k] = v;
           }
   #pragma unroll
           for (int k = 0; k < W; k++) eq |= (uint32_t)(pref[k] == pref[(k + 1) % W]) << k;
         };
-        if (KB == 8 && a.fix_cut >= 4) scan_window((uint32_t)0); else scan_window((O)0);
+        if (KB == 8 && cut_bit >= 32) scan_window((uint32_t)0); else scan_window((O)0);
         // re-index by window position: bit j = slots (base-1+j, base+j) agree, j = 0 .. IPT; bit W-1 is the wrap
         eq = ((eq << rot) | (eq >> (W - rot))) & ((1u << (W - 1)) - 1u);
         uint32_t members = (eq | (eq >> 1)) & ((1u << IPT) - 1u);  // own slots with an equal neighbour
@@ -987,7 +1047,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           const int sl = __ffs(members) - 1;
           members &= members - 1;
           const int i = base + sl;
-          const KeyT kraw = kst[i];
+          const KeyT kraw = key_at(i);
           const O ok = to_ordered<KB>(kraw, ko);
           // neighbours known to be in the run from the window bits, then (rarely) beyond the window
           const uint32_t below = ~eq & ((2u << sl) - 1u);  // zero bits at or below sl stop the run on the left
@@ -998,21 +1058,21 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           // it takes to know that it is too long (nl + nr = run length - 1 for every member alike)
           if (nl == sl + 1 && nl + nr <= FIX_CAP) {  // includes slot base-1
             int j = i - nl - 1;
-            while (j >= 0 && nl + nr <= FIX_CAP && (((O)kst[j] ^ (O)kraw) & pmask) == 0) { nl++; j--; }
+            while (j >= 0 && nl + nr <= FIX_CAP && (((O)key_at(j) ^ (O)kraw) & pmask) == 0) { nl++; j--; }
           }
           if (nr == IPT - sl && nl + nr <= FIX_CAP) {  // includes slot base+IPT
             int j = i + nr + 1;
-            while (j < lim && nl + nr <= FIX_CAP && (((O)kst[j] ^ (O)kraw) & pmask) == 0) { nr++; j++; }
+            while (j < lim && nl + nr <= FIX_CAP && (((O)key_at(j) ^ (O)kraw) & pmask) == 0) { nr++; j++; }
           }
           int cl = 0, cr = 0;
           if (nl + nr > FIX_CAP) {
             // Too long to be ordered here: every member keeps its slot and checks its own (slot, slot+1) pair;
             // if none is out of order the run is in order as it stands (duplicates of one key, typically)
             // and nobody has to be told.
-            if (((eq >> (sl + 1)) & 1u) && to_ordered<KB>(kst[i + 1], ko) < ok && ld_relaxed_u32(a.fix_flag) == 0) atomicOr(a.fix_flag, 1u);
+            if (((eq >> (sl + 1)) & 1u) && to_ordered<KB>(key_at(i + 1), ko) < ok && ld_relaxed_u32(a.fix_flag) == 0) atomicOr(a.fix_flag, 1u);
           } else {
-            for (int q = 1; q <= nl; q++) cl += to_ordered<KB>(kst[i - q], ko) > ok;
-            for (int q = 1; q <= nr; q++) cr += to_ordered<KB>(kst[i + q], ko) < ok;
+            for (int q = 1; q <= nl; q++) cl += to_ordered<KB>(key_at(i - q), ko) > ok;
+            for (int q = 1; q <= nr; q++) cr += to_ordered<KB>(key_at(i + q), ko) < ok;
           }
           if (cr != cl) sdelta[i] = (int8_t)(cr - cl);
         }
@@ -1069,8 +1129,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
 
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * TILE * a.stage_bytes);
-  uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + NWARPS * RADIX) + RADIX * 8 +
-                                                 RADIX * 4 + 32 * 4 + TILE * 3);
+  uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + NWARPS * RADIX) + RADIX * 8);  // = s_prefix
   // One tile per CTA.  (A persistent grid that loops over tickets was measured 17 % slower: CTAs that
   // start together stay in phase, so loads, look-backs and stores of the whole machine bunch up; fresh
   // CTAs per tile stagger naturally.  profiles/README.md)

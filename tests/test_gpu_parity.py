@@ -324,3 +324,99 @@ def test_hybrid_aos_and_multi_stream():
         assert np.array_equal(pb_, pa.astype(np.float64)) and np.array_equal(pc, (pa % 65536).astype(np.uint16))
     finally:
         S.set_option("algo", 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Large-sort flow (host reads the plan back; the last pass orders tile-local segments, junction_fix_kernel
+# the tile-straddling ones): forced at test sizes with host_plan_min_log2 = 0
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,margin", [(300_000, 2), ((1 << 20) + 77, 2), ((1 << 20) + 77, -2), ((1 << 20) + 77, -5)])
+def test_hybrid_host_plan_tile_local_ordering_and_junctions(n, margin):
+    rng = np.random.default_rng(n + margin)
+    try:
+        S.set_option("algo", 2)
+        S.set_option("host_plan_min_log2", 0)
+        S.set_option("margin_bits", margin)
+        for name, keys, dt in _hybrid_cases(n, rng):
+            keys = np.ascontiguousarray(keys.astype(dt))
+            for up in (True, False):
+                idx = np.arange(n, dtype=np.uint32)
+                k, (p,) = gpu_sort_soa(keys, [idx], up)
+                want = O.total_order_sorted_keys(keys, up)
+                assert k.tobytes() == want.tobytes(), (name, n, up)
+                assert np.array_equal(np.sort(p), idx) and keys[p].tobytes() == k.tobytes(), (name, n, up)
+            if name == "uniform_u64" and margin == 2:
+                st = S.last_stats()  # no full segment finish: the last pass and the junction kernel did it
+                assert st["algo"] == 2 and st["fell_back"] == 0 and st["cut_digit"] >= 2 and st["segfix_passes"] == 0
+    finally:
+        S.set_option("algo", 0)
+        S.set_option("host_plan_min_log2", 24)
+        S.set_option("margin_bits", 2)
+
+
+def test_hybrid_host_plan_aos_and_multi_stream():
+    n = (1 << 19) + 4099
+    rng = np.random.default_rng(77)
+    try:
+        S.set_option("algo", 2)
+        S.set_option("host_plan_min_log2", 0)
+        S.set_option("margin_bits", -2)  # about four keys per final segment: plenty of runs and junctions
+        for rec_bytes in (16, 32, 64):
+            keys = rng.integers(-2**63, 2**63 - 1, size=n, dtype=np.int64)
+            keys[::5] = keys[1::5][: len(keys[::5])]  # duplicates
+            rec = np.zeros((n, rec_bytes), np.uint8)
+            rec[:, :8] = keys.view(np.uint8).reshape(n, 8)
+            rec[:, 8:16] = np.arange(n, dtype=np.int64).view(np.uint8).reshape(n, 8)
+            if rec_bytes > 16:
+                rec[:, 16:] = (np.arange(n)[:, None] * 7 + np.arange(rec_bytes - 16)[None, :]).astype(np.uint8)
+            for up in (True, False):
+                r = dev(rec)
+                S.sort_combined(n, r, np.int64, up=up)
+                out = host(r)
+                ok = np.ascontiguousarray(out[:, :8]).reshape(-1).view(np.int64)
+                op = np.ascontiguousarray(out[:, 8:16]).reshape(-1).view(np.int64)
+                assert ok.tobytes() == O.total_order_sorted_keys(keys, up).tobytes(), (rec_bytes, up)
+                assert np.array_equal(np.sort(op), np.arange(n)) and np.array_equal(keys[op], ok)
+                assert np.array_equal(out, rec[op]), (rec_bytes, up)  # whole records travelled
+        fk = rng.uniform(-1, 1, size=n)
+        a, b, c = np.arange(n, dtype=np.int32), np.arange(n, dtype=np.float64), (np.arange(n) % 65536).astype(np.uint16)
+        for up in (True, False):
+            k, (pa, pb_, pc) = gpu_sort_soa(fk, [a, b, c], up)
+            assert k.tobytes() == O.total_order_sorted_keys(fk, up).tobytes() and fk[pa].tobytes() == k.tobytes()
+            assert np.array_equal(pb_, pa.astype(np.float64)) and np.array_equal(pc, (pa % 65536).astype(np.uint16))
+    finally:
+        S.set_option("algo", 0)
+        S.set_option("host_plan_min_log2", 24)
+        S.set_option("margin_bits", 2)
+
+
+@pytest.mark.parametrize("host_plan", [0, 24])
+def test_hybrid_left_shift_plan_for_common_leading_bits(host_plan):
+    """keys that agree on a few leading bits (a shard of a multi-GPU sort): the plan shifts them out and
+    needs one pass less; same result either way"""
+    n = 3 << 18
+    rng = np.random.default_rng(9)
+    body = rng.integers(0, 2**58, size=n, dtype=np.uint64)
+    passes = {}
+    try:
+        S.set_option("algo", 2)
+        S.set_option("host_plan_min_log2", host_plan)
+        S.set_option("margin_bits", -1)
+        for name, keys in (("u64_top6", body | np.uint64(0b101011 << 58)),
+                           ("i64_neg", (body | np.uint64(0b111111 << 58)).view(np.int64)),
+                           ("f64", (body >> np.uint64(2) | np.uint64(0x3FF << 52)).view(np.float64))):
+            keys = np.ascontiguousarray(keys)
+            for allow in (1, 0):
+                S.set_option("allow_lshift", allow)
+                for up in (True, False):
+                    idx = np.arange(n, dtype=np.uint32)
+                    k, (p,) = gpu_sort_soa(keys, [idx], up)
+                    assert k.tobytes() == O.total_order_sorted_keys(keys, up).tobytes(), (name, allow, up)
+                    assert np.array_equal(np.sort(p), idx) and keys[p].tobytes() == k.tobytes(), (name, allow, up)
+                passes[(name, allow)] = S.last_stats()["passes_planned"]
+        assert passes[("u64_top6", 1)] < passes[("u64_top6", 0)], passes
+    finally:
+        S.set_option("algo", 0)
+        S.set_option("allow_lshift", 1)
+        S.set_option("host_plan_min_log2", 24)
+        S.set_option("margin_bits", 2)
