@@ -139,11 +139,15 @@ typedef struct b200sort_comm b200sort_comm;
 int b200sort_mgpu_unique_id(void *out_id_128_bytes);
 int b200sort_mgpu_comm_create(b200sort_comm **out, int world_size, int rank, const void *id_128_bytes);
 int b200sort_mgpu_comm_destroy(b200sort_comm *comm);
+/* 1 if the last b200sort_mgpu_sort_soa on this communicator scattered its records straight into the peers'
+ * memory (cudaIpc-mapped workspaces over NVLink), 0 if it exchanged them with ncclSend/ncclRecv. */
+int b200sort_mgpu_used_p2p(const b200sort_comm *comm);
 
 /* Host-side splitter selection used by the multi-GPU sort (exported so that it can be tested without
  * a GPU): given the globally reduced histogram of the top `bits` bits of the order-mapped keys
  * (2^bits counters), writes world_size+1 bin boundaries b[0]=0 <= ... <= b[world]=2^bits such that
- * rank r owns bins [b[r], b[r+1]) and the loads are as even as bin granularity allows. */
+ * rank r owns bins [b[r], b[r+1]) and the loads are even to within bin granularity plus 1/64 of a share,
+ * which a boundary may give up to land on an aligned bin index (shards then share leading key bits). */
 int b200sort_mgpu_splitters(const uint64_t *global_hist, int bits, int world_size, uint32_t *out_bounds);
 
 /* Host-side exchange plan (also exported for GPU-less tests): number of local records destined to each

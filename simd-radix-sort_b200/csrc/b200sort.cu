@@ -10,6 +10,8 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
+#include <utility>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -44,6 +46,7 @@ static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 static std::atomic<int64_t> opt_probe_guess{1};
 static std::atomic<int64_t> opt_allow_lshift{1};
+static std::atomic<int64_t> opt_mgpu_p2p{1};  // multi-GPU: scatter straight into peer memory (0: NCCL send/recv)
 static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at least 2^this records read the plan back
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
@@ -115,10 +118,11 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
-static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false) {
+static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false, bool lut = false) {
   const size_t tile = (size_t)c.threads * c.ipt;
   return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 +
-         (fix ? tile : 0);  // FIX: per-slot displacement
+         (fix ? tile : 0) +       // FIX: per-slot displacement
+         (lut ? RADIX * 8 : 0);   // LUT: peer byte offsets
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
@@ -148,7 +152,7 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
     case 4: k = sweep_fn_kb4(cfg, nstage, any, lut, fix); break;
     default: k = sweep_fn_kb8(cfg, nstage, any, lut, fix); break;
   }
-  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix);
+  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
@@ -287,8 +291,10 @@ static uint32_t chunk_for(const void *p, uint32_t elem) {
 }
 
 // Sort arrays that are all in device memory.  streams[0] carries the key at offset 0.
+// start_sel = 1: the input lies in the workspace's shadow arrays (the multi-GPU exchange delivered it there), the
+// result still goes to the caller's arrays; layout_n: lay the workspace out for this many records (>= n)
 static int sort_device(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams,
-                       cudaStream_t stream, void *workspace, size_t workspace_bytes) {
+                       cudaStream_t stream, void *workspace, size_t workspace_bytes, int start_sel = 0, int64_t layout_n = 0) {
   const int kb = key_bytes_of(key_type);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -317,7 +323,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   if (smem > di.smem_optin) return fail(B200SORT_ECUDA, "device offers %zu B of shared memory, %zu needed", di.smem_optin, smem);
 
   Layout L;
-  make_layout(streams, n, std::min(tile, HYB_MIN_TILE), &L);
+  make_layout(streams, std::max(n, layout_n), std::min(tile, HYB_MIN_TILE), &L);
   void *const caller_workspace = workspace;
   if (workspace == nullptr) {
     if (int rc = cached_workspace(dev, L.total, &workspace)) return rc;
@@ -356,7 +362,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     uint64_t *ghist_exact = (uint64_t *)(ws + L.ghist2_off);
     ProbeOut *probe = (ProbeOut *)(ws + L.probe_off);
     HistArgs ha{};
-    ha.keys = ss.streams[0].buf[0];
+    ha.keys = ss.streams[0].buf[start_sel];
     ha.stride = streams[0].elem_bytes;
     ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
     const bool big = hybrid && n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);  // the host reads the plan back
@@ -393,6 +399,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     sa.margin_bits = (float)opt_margin_bits.load();
     sa.have_minmax = (int)ha.with_minmax;
     sa.allow_lshift = (int)opt_allow_lshift.load();
+    sa.start_sel = (uint32_t)start_sel;
     sa.guess_p1 = ha.guess_p1; sa.ghist_exact = ghist_exact;
     auto launch_scan = [&]() -> int {
       {
@@ -536,7 +543,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
         // a long bucket with distinct keys: finish with the plain digit-by-digit path (the array is a
         // permutation of the input, already ordered by its top digits)
         const int64_t saved = opt_algo.exchange(1);
-        const int rc = sort_device(key_type, ascending, n, streams, stream, caller_workspace, workspace_bytes);
+        const int rc = sort_device(key_type, ascending, n, streams, stream, caller_workspace, workspace_bytes, 0, layout_n);
         opt_algo.store(saved);
         if (rc != 0) return rc;
         b200sort_stats s2 = g_last_stats;
@@ -725,6 +732,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
   if (!strcmp(name, "probe_guess")) return &opt_probe_guess;
   if (!strcmp(name, "allow_lshift")) return &opt_allow_lshift;
+  if (!strcmp(name, "mgpu_p2p")) return &opt_mgpu_p2p;
   if (!strcmp(name, "host_plan_min_log2")) return &opt_host_plan_min_log2;
   if (!strcmp(name, "nstage")) return &opt_nstage;
   return nullptr;

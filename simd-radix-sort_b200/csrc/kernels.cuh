@@ -436,6 +436,7 @@ struct ScanArgs {
   float margin_bits;       // hybrid: sweep top digits until their entropies sum to log2(n) + margin_bits
   int have_minmax;         // 1: probe->max_key / nmin_key are valid
   int allow_lshift;        // 1: the plan may shift the keys left by their common leading bits
+  uint32_t start_sel;      // side of the ping-pong that holds the input (0 = the caller's arrays)
   uint32_t guess_p1;       // digit position + 1 probe_kernel counted exactly into ghist_exact (0 = none)
   uint64_t *ghist_exact;
 };
@@ -561,7 +562,7 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
     a.plan->sub = sub;
     a.plan->lshift = lshift;
     a.plan->want_minmax = want_minmax;
-    uint32_t sel = 0, n_exec = 0;
+    uint32_t sel = a.start_sel, n_exec = 0;
     int prev = -1;
     a.plan->first_exec_p1 = 0;
     for (int p = 0; p < a.n_passes; p++) {
@@ -615,6 +616,9 @@ struct SweepArgs {
   // top lut_bits bits of the ordered key (lut has 2^lut_bits entries), not a radix digit
   const uint8_t *lut;
   int lut_shift;
+  // ... and bucket d is written at byte offset peer_delta[d] from this GPU's own destination arrays: the
+  // same array in the workspace of GPU d, mapped into this process (nullptr: everything stays local)
+  const int64_t *peer_delta;
   uint32_t spin_ns;        // look-back back-off (option "spin_ns"), 0 = busy poll
   // When the host has read the plan back (large sorts) it passes what this pass needs as arguments, so a
   // CTA does not start with a dependent global load (244 K CTAs per pass at 1e9 records).
@@ -713,12 +717,22 @@ __device__ __forceinline__ void stage_sync(const unsigned char *src, unsigned ch
 
 // goff[k] is the destination element index of staged slot tid + k*THREADS (computed once per tile,
 // shared by all streams): consecutive threads write consecutive addresses of each bucket.
-template <typename T, int THREADS, int IPT, bool FULL>
+template <typename T, int THREADS, int IPT, bool FULL, bool PEER = false>
 __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const int64_t (&goff)[IPT], int n_valid,
-                                          uint32_t cpe, uint32_t c) {
+                                          uint32_t cpe, uint32_t c, const uint8_t *sdigit = nullptr, const int64_t *pdelta = nullptr) {
   const T *stage = reinterpret_cast<const T *>(buf) + threadIdx.x;
   T *d = reinterpret_cast<T *>(dst) + c;
-  if (cpe == 1) {  // one chunk per element (the common shapes): no index multiply
+  if constexpr (PEER) {
+    // partition pass of the multi-GPU sort: the bucket is a destination GPU, its arrays are peer memory
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const int i = (int)threadIdx.x + k * THREADS;
+      if (FULL || i < n_valid) {
+        T *dp = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(d) + pdelta[sdigit[i]]);
+        dp[(size_t)goff[k] * cpe] = stage[k * THREADS];
+      }
+    }
+  } else if (cpe == 1) {  // one chunk per element (the common shapes): no index multiply
 #pragma unroll
     for (int k = 0; k < IPT; k++)
       if (FULL || (int)threadIdx.x + k * THREADS < n_valid) d[goff[k]] = stage[k * THREADS];
@@ -746,6 +760,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   uint32_t *nhist = s_prefix;  // RADIX, zeroed by the kernel: the next digit's counts live here until thread d has
                                // read nhist[d], just before it writes s_prefix[d]
   int8_t *sdelta = reinterpret_cast<int8_t *>(sdigit + TILE);                                // TILE (FIX only): slot displacement
+  int64_t *pdelta = reinterpret_cast<int64_t *>(sdigit + TILE);                              // RADIX (LUT only): peer byte offsets
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile_base = tile * TILE;
@@ -893,6 +908,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     s_prefix[tid] += off;
     // counts published to other tiles exclude the padding of the last tile
     valid_count = my_count - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
+    if constexpr (LUT) pdelta[tid] = a.peer_delta ? a.peer_delta[tid] : 0;
     uint64_t *slot = &a.lookback[(size_t)tile * RADIX + tid];
     if (tile == 0)
       st_relaxed_u64(slot, LB_FLAG_PREFIX | tagbits | (tile0_base + valid_count));
@@ -1095,11 +1111,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       unsigned char *dst = st.buf[sel ^ 1];
       const unsigned char *buf = bufs[NSTAGE == 2 ? (j & 1) : 0];
       const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
-      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
-      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
-      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
-      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
-      else write_out<uint8_t, THREADS, IPT, FULL>(dst, buf, goff, n_valid, cpe, wr_c);
+      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
+      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
+      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
+      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
+      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
       if (++wr_c == cpe) { wr_c = 0; wr_s++; }
     }
     if (wr_s >= a.ss.n_streams) break;

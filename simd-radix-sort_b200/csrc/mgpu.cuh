@@ -1,12 +1,16 @@
 // mgpu.cuh -- multi-GPU sort: MSB range partition over the GPUs of one box.
 // Included at the end of b200sort.cu (it uses that file's internals).
 //
-//   1. every rank histograms the top bits of its order-mapped keys        (top_hist_kernel)
+//   1. every rank histograms the top 16 bits of a sample of its order-mapped keys (top_hist_kernel)
 //   2. ncclAllReduce(sum) of the histograms -> identical splitters on every rank (b200sort_mgpu_splitters)
-//   3. ncclAllGather of the per-destination send counts -> receive offsets
-//   4. local partition by destination rank = one scatter pass of onesweep_kernel in LUT mode
-//   5. all-to-all-v: grouped ncclSend/ncclRecv per peer for the keys and every payload stream
-//   6. local sort of the received range (sort_device)
+//   3. exact number of records per destination (dest_count_kernel); ncclAllGather of these rows together
+//      with every rank's workspace IPC handle -> receive offsets, peer mappings
+//   4. partition + exchange in ONE kernel: a scatter pass of onesweep_kernel in LUT mode whose bucket d is
+//      the receive region of GPU d -- the records leave the staging tile as coalesced stores straight
+//      into peer memory over NVLink (cudaIpc mapping of the peer's workspace); a 1-element all-reduce is
+//      the barrier after it.  Fallback when the workspaces cannot be mapped (or option mgpu_p2p = 0): the
+//      same pass into local memory, then grouped ncclSend/ncclRecv per peer.
+//   5. local sort of the received range, which starts in the workspace's shadow arrays (sort_device)
 // The reference has nothing here (single thread); NCCL is loaded lazily with dlopen so that the
 // single-GPU library has no NCCL dependency.
 #pragma once
@@ -66,17 +70,22 @@ struct TopHistArgs {
   KeyOrder ko;
   int shift;            // ordered key >> shift = bin
   unsigned long long *hist;  // [2^bits], zeroed
+  int64_t sample;       // every sample-th row of 32 keys is counted
 };
 
 template <int KB>
 __global__ void __launch_bounds__(256) top_hist_kernel(TopHistArgs a) {
-  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_round = (a.n + 31) / 32 * 32;  // keep warps converged for the ballot
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gsz) {
+  // every sample-th row of 32 consecutive keys (splitters only need proportions; the exact numbers of
+  // records per destination are counted afterwards by dest_count_kernel)
+  const int lane = threadIdx.x & 31;
+  const int64_t n_rows = (a.n + 31) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x / 32);
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * a.sample < n_rows; w += n_warps) {
+    const int64_t i = w * a.sample * 32 + lane;
     const bool valid = i < a.n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     if (valid) {
-      const uint32_t bin = (uint32_t)(to_ordered<KB>(load_key<KB>(a.keys, i, a.stride), a.ko) >> a.shift);
+      const uint32_t bin = (uint32_t)(to_ordered<KB, false>(load_key<KB>(a.keys, i, a.stride), a.ko) >> a.shift);
       const unsigned peers = __match_any_sync(vmask, bin);
       if ((peers & lanemask_lt()) == 0) atomicAdd(&a.hist[bin], (unsigned long long)__popc(peers));
     }
@@ -84,7 +93,9 @@ __global__ void __launch_bounds__(256) top_hist_kernel(TopHistArgs a) {
 }
 
 static cudaError_t launch_top_hist(int kb, const TopHistArgs &a, int sm_count, cudaStream_t st) {
-  const int grid = (int)std::min<int64_t>((a.n + 255) / 256, (int64_t)sm_count * 16);
+  const int64_t rows = ((a.n + 31) / 32 + a.sample - 1) / a.sample;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count * 16));
+  ProfScope ps(PK_HIST, st);
   switch (kb) {
     case 1: top_hist_kernel<1><<<grid, 256, 0, st>>>(a); break;
     case 2: top_hist_kernel<2><<<grid, 256, 0, st>>>(a); break;
@@ -95,39 +106,155 @@ static cudaError_t launch_top_hist(int kb, const TopHistArgs &a, int sm_count, c
   return cudaGetLastError();
 }
 
-// Greedy splitters on bin boundaries: rank r ends at the first boundary where the running count
-// reaches (r+1)/world of the total.  Identical on every rank because the input is the reduced histogram.
+// exact number of records this rank sends to every destination (destination = lut[top bits])
+struct DestCountArgs {
+  const unsigned char *keys;
+  uint32_t stride;
+  int64_t n;
+  KeyOrder ko;
+  int shift;
+  const uint8_t *lut;
+  unsigned long long *counts;  // [RADIX], zeroed
+};
+
+template <int KB, int NLD>
+__global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_kernel(DestCountArgs a) {
+  using KT = KeyTile<KB, HIST_THREADS, NLD>;
+  __shared__ uint32_t sh[RADIX];
+  for (int i = threadIdx.x; i < RADIX; i += HIST_THREADS) sh[i] = 0;
+  __syncthreads();
+  const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    KT kt;
+    kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);
+#pragma unroll
+    for (int i = 0; i < KT::PER_THREAD; i++) {
+      const bool v = (kt.valid >> i) & 1;
+      const unsigned vmask = __ballot_sync(0xffffffffu, v);
+      if (v) hist_add<true>(sh, (uint32_t)a.lut[(uint32_t)(kt.u[i] >> a.shift)], vmask);  // few destinations: aggregate
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RADIX; i += HIST_THREADS) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(&a.counts[i], (unsigned long long)c);
+  }
+}
+
+static cudaError_t launch_dest_count(int kb, const DestCountArgs &a, int sm_count, cudaStream_t st) {
+  const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a.n + tile_keys - 1) / tile_keys, (int64_t)sm_count * 8));
+  ProfScope ps(PK_HIST, st);
+  switch (kb) {
+    case 1: dest_count_kernel<1, hist_nld(1)><<<grid, HIST_THREADS, 0, st>>>(a); break;
+    case 2: dest_count_kernel<2, hist_nld(2)><<<grid, HIST_THREADS, 0, st>>>(a); break;
+    case 4: dest_count_kernel<4, hist_nld(4)><<<grid, HIST_THREADS, 0, st>>>(a); break;
+    default: dest_count_kernel<8, hist_nld(8)><<<grid, HIST_THREADS, 0, st>>>(a); break;
+  }
+  g_launches++;
+  return cudaGetLastError();
+}
+
+// Splitters on bin boundaries.  Rank r ideally ends where the running count reaches r/world of the total; any
+// boundary whose prefix is within 1/64 of a rank's share of that target is acceptable (capacities leave
+// 1/8), and among those the one with the most trailing zero bits wins: the keys of a shard then agree on as
+// many leading bits as possible (for uniform keys and a power-of-two world: exactly log2(world) bits),
+// which is what lets the local sort shift them out (Plan::lshift).  Identical on every rank because the
+// input is the reduced histogram.
 static void compute_splitters(const uint64_t *hist, int bits, int world, uint32_t *bounds) {
   const uint32_t nb = 1u << bits;
-  uint64_t total = 0;
-  for (uint32_t b = 0; b < nb; b++) total += hist[b];
+  std::vector<uint64_t> prefix((size_t)nb + 1);
+  prefix[0] = 0;
+  for (uint32_t b = 0; b < nb; b++) prefix[b + 1] = prefix[b] + hist[b];
+  const uint64_t total = prefix[nb];
+  const uint64_t tol = total / (uint64_t)world / 64;
   bounds[0] = 0;
-  uint64_t run = 0;
-  uint32_t b = 0;
   for (int r = 1; r < world; r++) {
-    // smallest boundary whose prefix is >= ceil(total * r / world), but never before the previous one
-    const uint64_t target = (uint64_t)(((unsigned __int128)total * (unsigned)r + (unsigned)world - 1) / (unsigned)world);
-    while (b < nb && run < target) run += hist[b++];
-    // choose the closer of the boundary just before and just after the target (bin granularity)
-    if (b > bounds[r - 1] + 0u && b > 0) {
-      const uint64_t over = run - target, under = target - (run - hist[b - 1]);
-      if (under < over && b - 1 >= bounds[r - 1]) { run -= hist[b - 1]; b--; }
+    const uint64_t target = (uint64_t)(((unsigned __int128)total * (unsigned)r) / (unsigned)world);
+    // first boundary whose prefix reaches the target, then the closer of it and the one before
+    uint32_t b = (uint32_t)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+    if (b > nb) b = nb;
+    if (b > 0 && target - prefix[b - 1] < prefix[b] - target) b--;
+    if (b < bounds[r - 1]) b = bounds[r - 1];
+    // most aligned acceptable boundary around it
+    uint32_t best = b;
+    int best_tz = b ? __builtin_ctz(b) : 32;
+    for (int dir = -1; dir <= 1; dir += 2) {
+      for (int64_t c = (int64_t)b + dir; c >= (int64_t)bounds[r - 1] && c <= (int64_t)nb; c += dir) {
+        const uint64_t pc = prefix[(size_t)c];
+        const uint64_t dist = pc > target ? pc - target : target - pc;
+        if (dist > tol) break;
+        const int tz = c ? __builtin_ctz((uint32_t)c) : 32;
+        if (tz > best_tz) { best = (uint32_t)c; best_tz = tz; }
+      }
     }
-    bounds[r] = b;
+    bounds[r] = best;
   }
   bounds[world] = nb;
 }
 
 }  // namespace b200sort
 
+// what every rank tells the others before the exchange (all-gathered in one go)
+struct MgpuBlob {
+  cudaIpcMemHandle_t handle;        // its workspace allocation
+  unsigned long long ws_bytes;      // size of that allocation's layout (equal layouts <=> equal shadow offsets)
+  long long capacity;
+  unsigned long long p2p;           // 1: this rank is willing to use the peer-memory path
+  unsigned long long counts[b200sort::RADIX];  // records it sends to every destination
+};
+
 struct b200sort_comm {
   ncclComm_t comm = nullptr;
   int world = 0, rank = 0, dev = 0;
   unsigned long long *d_hist = nullptr;   // [2^16] local, then reduced in place
-  unsigned long long *d_counts = nullptr; // [world] send counts, [world*world] gathered
+  unsigned long long *d_counts = nullptr; // [world] send counts, [world*world] gathered (NCCL path scratch, barrier word)
   uint8_t *d_lut = nullptr;               // [2^16]
   uint64_t *d_bin_base = nullptr;         // [RADIX]
+  int64_t *d_peer_delta = nullptr;        // [RADIX]
+  MgpuBlob *d_blob = nullptr;             // [world]
   b200sort::Plan *d_plan = nullptr;
+  // peer workspaces mapped into this process (cudaIpcOpenMemHandle), keyed by the handle they were opened from
+  std::vector<cudaIpcMemHandle_t> peer_handle;
+  std::vector<void *> peer_base;
+  bool p2p_failed = false;                // mapping failed once: stay on the NCCL path
+  bool last_p2p = false;
+};
+
+// B200SORT_MGPU_TRACE=1: per-phase device times of every multi-GPU sort on stderr (adds a stream sync at the end)
+struct MgpuTrace {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<std::pair<const char *, cudaEvent_t>> ev;
+  explicit MgpuTrace(cudaStream_t s) : st(s) {
+    const char *e = getenv("B200SORT_MGPU_TRACE");
+    on = e && *e == '1';
+    mark("start");
+  }
+  void mark(const char *name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.emplace_back(name, e);
+  }
+  void report(int rank) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    std::string line = "[b200sort mgpu rank " + std::to_string(rank) + "]";
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      char buf[96];
+      snprintf(buf, sizeof buf, " %s=%.3f", ev[i].first, ms);
+      line += buf;
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+    fprintf(stderr, "%s total=%.3f ms\n", line.c_str(), tot);
+    for (auto &e : ev) cudaEventDestroy(e.second);
+    ev.clear();
+  }
 };
 
 extern "C" {
@@ -162,6 +289,11 @@ int b200sort_mgpu_comm_create(b200sort_comm **out, int world_size, int rank, con
   CUDA_TRY(cudaMalloc(&c->d_lut, (size_t)1 << MGPU_MAX_BITS));
   CUDA_TRY(cudaMalloc(&c->d_bin_base, sizeof(uint64_t) * RADIX));
   CUDA_TRY(cudaMalloc(&c->d_plan, sizeof(Plan)));
+  CUDA_TRY(cudaMalloc(&c->d_peer_delta, sizeof(int64_t) * RADIX));
+  CUDA_TRY(cudaMalloc(&c->d_blob, sizeof(MgpuBlob) * (size_t)world_size));
+  c->peer_handle.resize(world_size);
+  c->peer_base.assign(world_size, nullptr);
+  for (auto &h : c->peer_handle) memset(&h, 0, sizeof h);
   *out = c;
   return 0;
 }
@@ -170,10 +302,15 @@ int b200sort_mgpu_comm_destroy(b200sort_comm *c) {
   using namespace b200sort;
   if (!c) return 0;
   if (c->comm) nccl_api().CommDestroy(c->comm);
+  for (int p = 0; p < c->world; p++)
+    if (p != c->rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
   cudaFree(c->d_hist); cudaFree(c->d_counts); cudaFree(c->d_lut); cudaFree(c->d_bin_base); cudaFree(c->d_plan);
+  cudaFree(c->d_peer_delta); cudaFree(c->d_blob);
   delete c;
   return 0;
 }
+
+int b200sort_mgpu_used_p2p(const b200sort_comm *c) { return c && c->last_p2p ? 1 : 0; }
 
 int b200sort_mgpu_splitters(const uint64_t *global_hist, int bits, int world_size, uint32_t *out_bounds) {
   using namespace b200sort;
@@ -216,49 +353,10 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   DevInfo di;
   if (int rc = dev_info(c->dev, &di)) return rc;
   const KeyOrder ko = make_key_order(key_type, ascending != 0);
+  MgpuTrace trace(stream);
 
-  // 1-2: local histogram of the top bits, all-reduce
-  CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned long long) * nb, stream));
-  if (num_local > 0) {
-    TopHistArgs ha{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_hist};
-    CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream));
-  }
-  std::vector<uint64_t> local_hist(nb), global_hist(nb);
-  CUDA_TRY(cudaMemcpyAsync(local_hist.data(), c->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, stream));
-  NCCL_TRY(api.AllReduce(c->d_hist, c->d_hist, nb, ncclUint64, ncclSum, c->comm, stream));
-  CUDA_TRY(cudaMemcpyAsync(global_hist.data(), c->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, stream));
-  CUDA_TRY(cudaStreamSynchronize(stream));
-
-  // splitters (same on every rank), destination LUT, send counts
-  std::vector<uint32_t> bounds(world + 1);
-  compute_splitters(global_hist.data(), bits, world, bounds.data());
-  std::vector<uint8_t> lut(nb);
-  std::vector<uint64_t> send(world, 0);
-  for (int r = 0; r < world; r++)
-    for (uint32_t b = bounds[r]; b < bounds[r + 1]; b++) { lut[b] = (uint8_t)r; send[r] += local_hist[b]; }
-
-  // 3: all-gather the send-count rows -> full matrix m[src][dst]
-  CUDA_TRY(cudaMemcpyAsync(c->d_counts, send.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
-  NCCL_TRY(api.AllGather(c->d_counts, c->d_counts + world, world, ncclUint64, c->comm, stream));
-  std::vector<uint64_t> m((size_t)world * world);
-  CUDA_TRY(cudaMemcpyAsync(m.data(), c->d_counts + world, sizeof(uint64_t) * world * world, cudaMemcpyDeviceToHost, stream));
-  CUDA_TRY(cudaStreamSynchronize(stream));
-  int64_t recv_total = 0;
-  std::vector<int64_t> recv_off(world), send_off(world);
-  for (int s = 0; s < world; s++) { recv_off[s] = recv_total; recv_total += (int64_t)m[(size_t)s * world + c->rank]; }
-  {
-    int64_t o = 0;
-    for (int r = 0; r < world; r++) { send_off[r] = o; o += (int64_t)send[r]; }
-  }
-  // every rank can evaluate every rank's receive total, so all ranks fail together
-  for (int r = 0; r < world; r++) {
-    int64_t t = 0;
-    for (int s = 0; s < world; s++) t += (int64_t)m[(size_t)s * world + r];
-    if (t > capacity) return fail(B200SORT_ENOMEM, "rank %d would receive %lld records, capacity is %lld", r, (long long)t, (long long)capacity);
-  }
-
-  // workspace: shadow of every stream sized for max(num_local, recv_total)
-  const int64_t n_ws = std::max<int64_t>(std::max(num_local, recv_total), 1);
+  // workspace, laid out for `capacity` records on every rank (so that equal capacities give equal layouts
+  // and the local sort below finds what the peers wrote where it expects its shadow arrays)
   uint32_t stage_bytes = (uint32_t)kb;
   StreamSet ss{};
   ss.n_streams = (int)streams.size();
@@ -272,6 +370,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   const int cfg = pick_tile_cfg(kb, stage_bytes, di.smem_optin);
   const TileCfg tc = kTileCfgs[cfg];
   const int tile = tc.threads * tc.ipt;
+  const int64_t n_ws = std::max<int64_t>(capacity, 1);
   Layout L;
   make_layout(streams, n_ws, std::min(tile, HYB_MIN_TILE), &L);
   void *ws_v = nullptr;
@@ -279,45 +378,167 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   unsigned char *ws = (unsigned char *)ws_v;
   for (size_t s = 0; s < streams.size(); s++) ss.streams[s].buf[1] = ws + L.shadow_off[s];
 
-  // 4: partition by destination: one scatter pass, caller arrays -> shadow
+  // 1-2: histogram of the top bits of a sample of the local keys, all-reduce
+  CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned long long) * nb, stream));
   if (num_local > 0) {
+    TopHistArgs ha{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_hist,
+                   std::max<int64_t>(1, num_local >> 24)};  // about 2^24 sampled keys at most
+    CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream));
+  }
+  std::vector<uint64_t> global_hist(nb);
+  NCCL_TRY(api.AllReduce(c->d_hist, c->d_hist, nb, ncclUint64, ncclSum, c->comm, stream));
+  CUDA_TRY(cudaMemcpyAsync(global_hist.data(), c->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  trace.mark("hist+allreduce");
+
+  // splitters (same on every rank) -> destination LUT
+  std::vector<uint32_t> bounds(world + 1);
+  compute_splitters(global_hist.data(), bits, world, bounds.data());
+  std::vector<uint8_t> lut(nb);
+  for (int r = 0; r < world; r++)
+    for (uint32_t b = bounds[r]; b < bounds[r + 1]; b++) lut[b] = (uint8_t)r;
+  CUDA_TRY(cudaMemcpyAsync(c->d_lut, lut.data(), nb, cudaMemcpyHostToDevice, stream));
+
+  // 3: my blob = {workspace handle, layout size, capacity, exact send counts}; all-gather
+  MgpuBlob mine{};
+  const bool want_p2p = opt_mgpu_p2p.load() != 0 && !c->p2p_failed;
+  if (want_p2p) {
+    cudaError_t e = cudaIpcGetMemHandle(&mine.handle, ws);
+    if (e != cudaSuccess) { cudaGetLastError(); c->p2p_failed = true; }
+  }
+  mine.ws_bytes = L.total;
+  mine.capacity = capacity;
+  mine.p2p = (want_p2p && !c->p2p_failed) ? 1 : 0;
+  MgpuBlob *my_slot = c->d_blob + c->rank;
+  CUDA_TRY(cudaMemcpyAsync(my_slot, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));  // counts zeroed with it
+  if (num_local > 0) {
+    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts};
+    CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
+  }
+  NCCL_TRY(api.AllGather(my_slot, c->d_blob, sizeof(MgpuBlob), ncclUint8, c->comm, stream));
+  std::vector<MgpuBlob> blobs(world);
+  CUDA_TRY(cudaMemcpyAsync(blobs.data(), c->d_blob, sizeof(MgpuBlob) * world, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  trace.mark("count+allgather");
+
+  auto m = [&](int src, int dst) -> uint64_t { return blobs[src].counts[dst]; };
+  std::vector<uint64_t> send(world);
+  for (int r = 0; r < world; r++) send[r] = m(c->rank, r);
+  int64_t recv_total = 0;
+  std::vector<int64_t> recv_off(world), send_off(world);
+  for (int s = 0; s < world; s++) { recv_off[s] = recv_total; recv_total += (int64_t)m(s, c->rank); }
+  {
+    int64_t o = 0;
+    for (int r = 0; r < world; r++) { send_off[r] = o; o += (int64_t)send[r]; }
+  }
+  // every rank can evaluate every rank's receive total, so all ranks fail together
+  for (int r = 0; r < world; r++) {
+    int64_t t = 0;
+    for (int s = 0; s < world; s++) t += (int64_t)m(s, r);
+    if (t > blobs[r].capacity)
+      return fail(B200SORT_ENOMEM, "rank %d would receive %lld records, its capacity is %lld", r, (long long)t, (long long)blobs[r].capacity);
+  }
+
+  // peer-memory path: everybody willing, equal layouts; map the workspaces that changed since the last sort
+  bool p2p = true;
+  for (int r = 0; r < world; r++) p2p = p2p && blobs[r].p2p == 1 && blobs[r].ws_bytes == L.total && blobs[r].capacity == capacity;
+  if (p2p) {
+    bool ok = true;
+    for (int r = 0; r < world; r++) {
+      if (r == c->rank) { c->peer_base[r] = ws; continue; }
+      if (c->peer_base[r] && memcmp(&c->peer_handle[r], &blobs[r].handle, sizeof(cudaIpcMemHandle_t)) == 0) continue;
+      if (c->peer_base[r]) { cudaIpcCloseMemHandle(c->peer_base[r]); c->peer_base[r] = nullptr; }
+      void *pp = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&pp, blobs[r].handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { cudaGetLastError(); ok = false; continue; }
+      c->peer_base[r] = pp;
+      c->peer_handle[r] = blobs[r].handle;
+    }
+    // (the set of changed handles is the same on every rank up to a rank's own, so all ranks that see a
+    //  change agree below; a rank that sees none contributes "ok")
+    // agreement: one failed mapping anywhere sends everybody to the NCCL path for good
+    unsigned long long flag = ok ? 0ull : 1ull;
+    CUDA_TRY(cudaMemcpyAsync(c->d_counts, &flag, sizeof flag, cudaMemcpyHostToDevice, stream));
+    NCCL_TRY(api.AllReduce(c->d_counts, c->d_counts, 1, ncclUint64, ncclSum, c->comm, stream));
+    CUDA_TRY(cudaMemcpyAsync(&flag, c->d_counts, sizeof flag, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (flag != 0) { c->p2p_failed = true; p2p = false; }
+  }
+  trace.mark("map");
+  c->last_p2p = p2p;
+
+  // 4: partition by destination: one scatter pass; bucket d = what goes to rank d.
+  //    peer path : caller arrays -> shadow arrays OF RANK d, at the offset where this rank's records belong
+  //    NCCL path : caller arrays -> own shadow arrays, then send/recv
+  {
     CUDA_TRY(cudaMemsetAsync(ws + L.ctrl_off, 0, L.ctrl_bytes, stream));
     uint64_t bin_base[RADIX] = {0};
-    for (int r = 0; r < RADIX; r++) bin_base[r] = r < world ? (uint64_t)send_off[r] : (uint64_t)num_local;
+    int64_t peer_delta[RADIX] = {0};
+    for (int r = 0; r < RADIX; r++) {
+      if (r < world) {
+        if (p2p) {
+          int64_t o = 0;
+          for (int s2 = 0; s2 < c->rank; s2++) o += (int64_t)m(s2, r);  // my region inside rank r's receive range
+          bin_base[r] = (uint64_t)o;
+          peer_delta[r] = (int64_t)((intptr_t)c->peer_base[r] - (intptr_t)ws);
+        } else {
+          bin_base[r] = (uint64_t)send_off[r];
+        }
+      } else {
+        bin_base[r] = (uint64_t)num_local;
+      }
+    }
     Plan plan{};
     plan.final_sel = 1; plan.n_exec = 1;
-    CUDA_TRY(cudaMemcpyAsync(c->d_lut, lut.data(), nb, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(c->d_bin_base, bin_base, sizeof bin_base, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_peer_delta, peer_delta, sizeof peer_delta, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(c->d_plan, &plan, sizeof plan, cudaMemcpyHostToDevice, stream));
-    SweepArgs wa{};
-    wa.ss = ss; wa.n = num_local; wa.ko = ko; wa.pass = 0; wa.shift = 0;
-    wa.bin_base = c->d_bin_base; wa.lookback = (uint64_t *)(ws + L.lookback_off);
-    wa.tile_counter = (uint32_t *)(ws + L.tilectr_off); wa.plan = c->d_plan; wa.tag = 1; wa.stage_bytes = stage_bytes;
-    wa.lut = c->d_lut; wa.lut_shift = shift;
-    CUDA_TRY(launch_sweep(kb, cfg, wa, (num_local + tile - 1) / tile, di.smem_optin, di.sm_count, stream));
-    // bin_base / plan / lut live in the communicator and are reused: the copies above are stream-ordered,
-    // but the host arrays are stack/vector memory, so wait before they go out of scope
+    if (num_local > 0) {
+      SweepArgs wa{};
+      wa.ss = ss; wa.n = num_local; wa.ko = ko; wa.pass = 0; wa.shift = 0;
+      wa.bin_base = c->d_bin_base; wa.lookback = (uint64_t *)(ws + L.lookback_off);
+      wa.tile_counter = (uint32_t *)(ws + L.tilectr_off); wa.plan = c->d_plan; wa.tag = 1; wa.stage_bytes = stage_bytes;
+      wa.lut = c->d_lut; wa.lut_shift = shift;
+      wa.peer_delta = p2p ? c->d_peer_delta : nullptr;
+      CUDA_TRY(launch_sweep(kb, cfg, wa, (num_local + tile - 1) / tile, di.smem_optin, di.sm_count, stream));
+    }
+    // the host arrays above are stack memory; the copies are stream-ordered but pageable: wait before
+    // they go out of scope (this also bounds how far the host runs ahead of the exchange)
     CUDA_TRY(cudaStreamSynchronize(stream));
   }
+  trace.mark(p2p ? "partition+exchange" : "partition");
 
-  // 5: all-to-all-v, shadow -> caller arrays
-  NCCL_TRY(api.GroupStart());
-  for (size_t s = 0; s < streams.size(); s++) {
-    const size_t eb = streams[s].elem_bytes;
-    for (int p = 0; p < world; p++) {
-      const size_t sb = (size_t)send[p] * eb, rb = (size_t)m[(size_t)p * world + c->rank] * eb;
-      if (sb) NCCL_TRY(api.Send(ss.streams[s].buf[1] + (size_t)send_off[p] * eb, sb, ncclUint8, p, c->comm, stream));
-      if (rb) NCCL_TRY(api.Recv(ss.streams[s].buf[0] + (size_t)recv_off[p] * eb, rb, ncclUint8, p, c->comm, stream));
+  *out_num_local = recv_total;
+  if (p2p) {
+    // barrier: nobody reads its shadow arrays before every rank's scatter kernel has finished (the
+    // all-reduce is ordered after the local kernel on each rank's stream and completes when all joined)
+    NCCL_TRY(api.AllReduce(c->d_counts, c->d_counts, 1, ncclUint64, ncclSum, c->comm, stream));
+    trace.mark("barrier");
+    // 5: local sort, input in the shadow arrays, result in the caller's arrays
+    if (recv_total > 0) {
+      int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0, /*start_sel=*/1, /*layout_n=*/n_ws);
+      if (rc != 0) return rc;
+    }
+  } else {
+    // all-to-all-v, shadow -> caller arrays
+    NCCL_TRY(api.GroupStart());
+    for (size_t s = 0; s < streams.size(); s++) {
+      const size_t eb = streams[s].elem_bytes;
+      for (int p = 0; p < world; p++) {
+        const size_t sb = (size_t)send[p] * eb, rb = (size_t)m(p, c->rank) * eb;
+        if (sb) NCCL_TRY(api.Send(ss.streams[s].buf[1] + (size_t)send_off[p] * eb, sb, ncclUint8, p, c->comm, stream));
+        if (rb) NCCL_TRY(api.Recv(ss.streams[s].buf[0] + (size_t)recv_off[p] * eb, rb, ncclUint8, p, c->comm, stream));
+      }
+    }
+    NCCL_TRY(api.GroupEnd());
+    trace.mark("exchange");
+    if (recv_total > 1) {
+      int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0);
+      if (rc != 0) return rc;
     }
   }
-  NCCL_TRY(api.GroupEnd());
-
-  // 6: local sort of what arrived
-  *out_num_local = recv_total;
-  if (recv_total > 1) {
-    int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0);
-    if (rc != 0) return rc;
-  }
+  trace.mark("local_sort");
+  trace.report(c->rank);
   return 0;
 }
 

@@ -34,41 +34,55 @@ def main():
 
     cases = [(np.uint64, "Uniform", True, 1_000_003), (np.float32, "Gaussian", False, 400_000), (np.int16, "Uniform", True, 250_000),
              (np.int64, "Gaussian", True, 300_000), (np.float64, "Uniform", False, 2_000_000)]
-    for ci, (dt, distname, up, n_local) in enumerate(cases):
-        n_local += 1000 * rank
-        keys = O.make_keys(distname, dt, n_local, seed=100 * ci + rank)
-        pay = (np.arange(n_local, dtype=np.uint64) + (rank << 40))
-        cap = int(n_local * 1.5) + 4096
-        k = torch.zeros(cap, dtype=torch.from_numpy(keys[:1]).dtype, device=dev)
-        p = torch.zeros(cap, dtype=torch.uint64, device=dev)
-        k[:n_local].copy_(torch.from_numpy(keys))
-        p[:n_local].copy_(torch.from_numpy(pay))
-        ptrs = (ctypes.c_void_p * 1)(p.data_ptr())
-        sizes = (ctypes.c_uint32 * 1)(8)
-        got = ctypes.c_int64(0)
-        rc = L.b200sort_mgpu_sort_soa(comm, k.data_ptr(), S.KEY_TYPES[np.dtype(dt).name], n_local, cap, int(up), 1, ptrs, sizes,
-                                      ctypes.byref(got), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0, L.b200sort_last_error()
-        torch.cuda.synchronize()
-        m = got.value
-        out_k, out_p = k[:m].cpu().numpy(), p[:m].cpu().numpy()
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (keys, pay, out_k, out_p))
-        if rank == 0:
-            all_in_k = np.concatenate([g[0] for g in gathered])
-            all_in_p = np.concatenate([g[1] for g in gathered])
-            all_out_k = np.concatenate([g[2] for g in gathered])
-            all_out_p = np.concatenate([g[3] for g in gathered])
-            want = O.total_order_sorted_keys(all_in_k, up)
-            assert all_out_k.tobytes() == want.tobytes(), f"case {ci}: distributed key sequence differs"
-            # payload followed its key: payload encodes (source rank, source index)
-            src_rank, src_idx = all_out_p >> np.uint64(40), all_out_p & np.uint64((1 << 40) - 1)
-            offs = np.cumsum([0] + [len(g[0]) for g in gathered])[:-1]
-            pos = offs[src_rank.astype(np.int64)] + src_idx.astype(np.int64)
-            assert all_in_k[pos].tobytes() == all_out_k.tobytes(), f"case {ci}: payload did not follow its key"
-            assert np.array_equal(np.sort(pos), np.arange(len(all_in_k))), f"case {ci}: not a permutation"
-            sizes_out = [len(g[2]) for g in gathered]
-            assert max(sizes_out) <= 1.3 * (sum(sizes_out) / world) + 70000, f"case {ci}: unbalanced {sizes_out}"
+    L.b200sort_mgpu_used_p2p.argtypes = [ctypes.c_void_p]
+    for p2p in (1, 0):  # records scattered straight into peer memory / exchanged with ncclSend+ncclRecv
+        S.set_option("mgpu_p2p", p2p)
+        for ci, (dt, distname, up, n_base) in enumerate(cases):
+            n_local = n_base + 1000 * rank
+            keys = O.make_keys(distname, dt, n_local, seed=100 * ci + rank)
+            pay = (np.arange(n_local, dtype=np.uint64) + (rank << 40))
+            pay2 = (np.arange(n_local) % 65521).astype(np.uint16)  # a second, narrow payload stream
+            cap = int((n_base + 1000 * world) * 1.5) + 4096      # the same on every rank (peer path needs equal layouts)
+            k = torch.zeros(cap, dtype=torch.from_numpy(keys[:1]).dtype, device=dev)
+            p = torch.zeros(cap, dtype=torch.uint64, device=dev)
+            p2 = torch.zeros(cap, dtype=torch.uint16, device=dev)
+            k[:n_local].copy_(torch.from_numpy(keys))
+            p[:n_local].copy_(torch.from_numpy(pay))
+            p2[:n_local].copy_(torch.from_numpy(pay2))
+            ptrs = (ctypes.c_void_p * 2)(p.data_ptr(), p2.data_ptr())
+            sizes = (ctypes.c_uint32 * 2)(8, 2)
+            got = ctypes.c_int64(0)
+            for rep in range(2):  # twice: the second call reuses the mapped peer workspaces
+                if rep:
+                    k[:n_local].copy_(torch.from_numpy(keys))
+                    p[:n_local].copy_(torch.from_numpy(pay))
+                    p2[:n_local].copy_(torch.from_numpy(pay2))
+                rc = L.b200sort_mgpu_sort_soa(comm, k.data_ptr(), S.KEY_TYPES[np.dtype(dt).name], n_local, cap, int(up), 2, ptrs, sizes,
+                                              ctypes.byref(got), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, L.b200sort_last_error()
+                torch.cuda.synchronize()
+            assert L.b200sort_mgpu_used_p2p(comm) == p2p, f"case {ci}: path taken {L.b200sort_mgpu_used_p2p(comm)}, wanted {p2p}"
+            m = got.value
+            out_k, out_p, out_p2 = k[:m].cpu().numpy(), p[:m].cpu().numpy(), p2[:m].cpu().numpy()
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (keys, pay, out_k, out_p, out_p2))
+            if rank == 0:
+                all_in_k = np.concatenate([g[0] for g in gathered])
+                all_out_k = np.concatenate([g[2] for g in gathered])
+                all_out_p = np.concatenate([g[3] for g in gathered])
+                all_out_p2 = np.concatenate([g[4] for g in gathered])
+                want = O.total_order_sorted_keys(all_in_k, up)
+                assert all_out_k.tobytes() == want.tobytes(), f"case {ci} p2p={p2p}: distributed key sequence differs"
+                # payload followed its key: payload encodes (source rank, source index)
+                src_rank, src_idx = all_out_p >> np.uint64(40), all_out_p & np.uint64((1 << 40) - 1)
+                offs = np.cumsum([0] + [len(g[0]) for g in gathered])[:-1]
+                pos = offs[src_rank.astype(np.int64)] + src_idx.astype(np.int64)
+                assert all_in_k[pos].tobytes() == all_out_k.tobytes(), f"case {ci} p2p={p2p}: payload did not follow its key"
+                assert np.array_equal(np.sort(pos), np.arange(len(all_in_k))), f"case {ci} p2p={p2p}: not a permutation"
+                assert np.array_equal(all_out_p2, (src_idx % np.uint64(65521)).astype(np.uint16)), f"case {ci} p2p={p2p}: second payload"
+                sizes_out = [len(g[2]) for g in gathered]
+                assert max(sizes_out) <= 1.3 * (sum(sizes_out) / world) + 70000, f"case {ci}: unbalanced {sizes_out}"
+    S.set_option("mgpu_p2p", 1)
     dist.barrier()
     assert L.b200sort_mgpu_comm_destroy(comm) == 0
     dist.destroy_process_group()

@@ -92,7 +92,8 @@ def test_splitters_balance_and_cover():
         assert bounds[0] == 0 and bounds[-1] == (1 << bits) and np.all(np.diff(bounds.astype(np.int64)) >= 0)
         loads = np.array([hist[bounds[r]:bounds[r + 1]].sum() for r in range(world)], dtype=np.float64)
         ideal = hist.sum() / world
-        assert np.all(np.abs(loads - ideal) <= hist.max() + 1), (loads, ideal)
+        # each boundary may sit up to 1/64 of a share off its target in favour of an aligned bin index
+        assert np.all(np.abs(loads - ideal) <= ideal / 32 + hist.max() + 1), (loads, ideal)
     # skew: one bin holds everything -> one rank gets it all, the others nothing, still a cover
     hist = np.zeros(256, np.uint64)
     hist[17] = 1000

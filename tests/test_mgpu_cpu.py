@@ -63,8 +63,8 @@ WORKER = textwrap.dedent('''
         for r in range(world - 1):
             if edges[r][0] and edges[r + 1][0]:
                 assert edges[r][2][0] <= edges[r + 1][1][0], "rank ranges overlap"
-        # loads are balanced to bin granularity
-        assert max(e[0] for e in edges) <= total / world + global_hist.max() + 1
+        # loads are balanced to bin granularity plus the 1/64 share a boundary may give up for an aligned bin index
+        assert max(e[0] for e in edges) <= total / world * (1 + 1 / 32) + global_hist.max() + 1
     dist.barrier()
     dist.destroy_process_group()
     print("MGPU_CPU_OK", rank)
