@@ -5,8 +5,9 @@
 
 A "step" is one complete sort of one batch of synthetic records.
   N = 1 : BASELINE.json configs[1]: uint64 key + uint64 payload, 1e9 uniform-random records, ascending.
-  N > 1 : configs[4] (weak scaling): every rank holds 1e9 such records; one step = histogram ->
-          NCCL all-reduce -> splitters -> partition -> NCCL all-to-all -> local sort.
+  N > 1 : configs[4] (weak scaling): every rank holds 1e9 such records; one step = sampled top histogram ->
+          NCCL all-reduce -> splitters -> exact destination counts -> NCCL all-gather -> ONE scatter pass that
+          writes every record straight into its destination GPU's memory over NVLink -> local sort.
 `value` is device-resident throughput (records of all ranks / max-over-ranks CUDA-event time of the
 sort itself; the untimed copy that restores the unsorted input between steps is outside the events).
 `e2e` is the same sort through the public API with HOST (pinned) buffers, H2D + D2H inside the timing.
@@ -15,6 +16,7 @@ sort itself; the untimed copy that restores the unsorted input between steps is 
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -388,18 +390,24 @@ def main():
         dt, kind, sample, cores, used_n = cpu_sort_sample(args.cpu_sample)
         cpu = {"value": used_n / dt * 1e-9, "unit": "Gpairs/s", "cores": cores, "kind": kind, "sample": sample}
 
+    exchange = None
+    if multi:
+        S.lib().b200sort_mgpu_used_p2p.argtypes = [ctypes.c_void_p]
+        exchange = ("scatter pass writes straight into peer memory (cudaIpc-mapped workspaces)"
+                    if S.lib().b200sort_mgpu_used_p2p(comm) else "local scatter pass + ncclSend/ncclRecv")
     line = {
         "metric": METRIC, "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": ("uint64 key + uint64 payload, 1e9 uniform-random records on 1 B200 (BASELINE.json configs[1])"
                                 if not multi else
-                                f"uint64 key + uint64 payload, {world}e9 records sharded over {world} B200 with NCCL all-to-all "
+                                f"uint64 key + uint64 payload, {world}e9 records sharded over {world} B200, exchanged over NVLink "
                                 "(BASELINE.json configs[4], 1e9 per GPU)"),
                    "records_per_gpu": n, "record_bytes": RECORD_BYTES, "ascending": True,
                    "l2": "inputs (16 GB per GPU) are larger than L2; no flush needed",
                    "algo": {1: "LSD one-sweep", 2: "hybrid MSB"}.get(stats["algo"], "?"),
-                   "scatter_passes": stats["passes_planned"], "hist_sweeps": stats["hist_sweeps"]},
+                   "scatter_passes": stats["passes_planned"], "hist_sweeps": stats["hist_sweeps"],
+                   **({"exchange": exchange} if multi else {})},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

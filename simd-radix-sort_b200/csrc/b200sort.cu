@@ -46,6 +46,7 @@ static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 static std::atomic<int64_t> opt_probe_guess{1};
 static std::atomic<int64_t> opt_allow_lshift{1};
+static std::atomic<int64_t> opt_mgpu_landing{1};  // multi-GPU: receive into a third set of arrays (saves the final copy)
 static std::atomic<int64_t> opt_mgpu_p2p{1};  // multi-GPU: scatter straight into peer memory (0: NCCL send/recv)
 static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at least 2^this records read the plan back
 
@@ -248,6 +249,7 @@ struct StreamDesc { void *ptr; uint32_t elem_bytes; };
 
 struct Layout {
   size_t shadow_off[MAX_STREAMS];
+  size_t land_off[MAX_STREAMS];
   size_t ctrl_off, ctrl_bytes;       // zeroed at the start of every sort
   size_t ghist_off, ghist2_off, probe_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off;
   size_t total;
@@ -262,7 +264,7 @@ static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin) {
   return cfg;
 }
 
-static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int tile, Layout *L) {
+static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int tile, Layout *L, bool landing = false) {
   size_t off = 0;
   for (size_t s = 0; s < streams.size(); s++) {
     L->shadow_off[s] = off;
@@ -280,6 +282,12 @@ static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int t
   L->lookback_off = off;            off += (size_t)L->n_tiles * RADIX * 8;
   L->ctrl_bytes = off - L->ctrl_off;
   L->binbase_off = off;             off += (size_t)MAX_PASSES * RADIX * 8;
+  off = align_up(off, 256);
+  // multi-GPU: a third copy of every stream, where the peers deliver this rank's records (see mgpu.cuh)
+  for (size_t s = 0; s < streams.size(); s++) {
+    L->land_off[s] = off;
+    if (landing) off = align_up(off + (size_t)n * streams[s].elem_bytes, 256);
+  }
   L->total = align_up(off, 256);
 }
 
@@ -291,10 +299,20 @@ static uint32_t chunk_for(const void *p, uint32_t elem) {
 }
 
 // Sort arrays that are all in device memory.  streams[0] carries the key at offset 0.
-// start_sel = 1: the input lies in the workspace's shadow arrays (the multi-GPU exchange delivered it there), the
-// result still goes to the caller's arrays; layout_n: lay the workspace out for this many records (>= n)
+struct DevSortOpts {
+  int start_sel = 0;         // 1: the input lies in the workspace's shadow arrays, the result still goes to the caller's
+  int64_t layout_n = 0;      // lay the workspace out for this many records (>= n)
+  int hint_lead_bits = 0;    // leading bits the caller expects all keys to agree on (steers the probe's guess)
+  bool layout_landing = false;  // the layout has landing arrays (make_layout(..., landing))
+  bool landing_input = false;   // the input lies in the landing arrays: the first executed pass reads it from
+                                // there (landing -> shadow -> caller -> ...), so that an even number of passes
+                                // ends in the caller's arrays without a copy
+};
 static int sort_device(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams,
-                       cudaStream_t stream, void *workspace, size_t workspace_bytes, int start_sel = 0, int64_t layout_n = 0) {
+                       cudaStream_t stream, void *workspace, size_t workspace_bytes, const DevSortOpts &xo = DevSortOpts()) {
+  const int start_sel = xo.start_sel;
+  const int64_t layout_n = xo.layout_n;
+  const int hint_lead_bits = xo.hint_lead_bits;
   const int kb = key_bytes_of(key_type);
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -323,7 +341,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   if (smem > di.smem_optin) return fail(B200SORT_ECUDA, "device offers %zu B of shared memory, %zu needed", di.smem_optin, smem);
 
   Layout L;
-  make_layout(streams, std::max(n, layout_n), std::min(tile, HYB_MIN_TILE), &L);
+  make_layout(streams, std::max(n, layout_n), std::min(tile, HYB_MIN_TILE), &L, xo.layout_landing);
   void *const caller_workspace = workspace;
   if (workspace == nullptr) {
     if (int rc = cached_workspace(dev, L.total, &workspace)) return rc;
@@ -361,11 +379,26 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     //      scatter pass per digit position (skipped ones return at once), segment finish, copy-back ----
     uint64_t *ghist_exact = (uint64_t *)(ws + L.ghist2_off);
     ProbeOut *probe = (ProbeOut *)(ws + L.probe_off);
+    const bool big = hybrid && n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);  // the host reads the plan back
+    // Input in the landing arrays (multi-GPU): only the large hybrid flow knows on the host which pass runs
+    // first; everything else simply starts with a copy into the caller's arrays.
+    bool landing = xo.landing_input;
+    auto copy_landing_to_caller = [&]() -> int {
+      for (size_t s2 = 0; s2 < streams.size(); s2++)
+        CUDA_TRY(cudaMemcpyAsync(streams[s2].ptr, ws + L.land_off[s2], (size_t)n * streams[s2].elem_bytes, cudaMemcpyDeviceToDevice, stream));
+      return 0;
+    };
+    if (landing && !big) {
+      if (int rc = copy_landing_to_caller()) return rc;
+      landing = false;
+    }
+    StreamSet ss_in = ss;  // what the key sweeps and the first executed pass read
+    if (landing)
+      for (size_t s2 = 0; s2 < streams.size(); s2++) ss_in.streams[s2].buf[0] = ws + L.land_off[s2];
     HistArgs ha{};
-    ha.keys = ss.streams[0].buf[start_sel];
+    ha.keys = ss_in.streams[0].buf[start_sel];
     ha.stride = streams[0].elem_bytes;
     ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
-    const bool big = hybrid && n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);  // the host reads the plan back
     {
       const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
       // entropies from one key per thread of every 8th tile once there are plenty of tiles
@@ -379,13 +412,16 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     // The digit position the first pass will sweep if the keys are (close to) uniformly distributed: the
     // probe counts it exactly, and if the plan comes out that way hist_kernel is not needed.
     {
-      uint32_t guess = 0;
+      uint32_t guess = 0, guess_l = 0;
       if (hybrid) {
+        // hint_lead_bits: leading bits the caller expects all keys to agree on (a shard of the multi-GPU sort)
         const double need = std::log2((double)n) + (double)opt_margin_bits.load();
         const int swept = (int)std::ceil(need / 8.0);
-        const int cut = 8 - swept;
-        guess = cut >= 2 ? (uint32_t)cut : 0;
+        const int shift_l = opt_allow_lshift.load() != 0 ? (hint_lead_bits & 7) : 0;
+        const int cut = 8 - hint_lead_bits / 8 - swept;
+        if (cut >= 2) { guess = (uint32_t)cut; guess_l = (uint32_t)shift_l; }
       }
+      ha.guess_lshift = guess_l;
       ha.guess_p1 = opt_probe_guess.load() != 0 ? guess + 1 : 0;
       ha.ghist_exact = ghist_exact;
     }
@@ -400,7 +436,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     sa.have_minmax = (int)ha.with_minmax;
     sa.allow_lshift = (int)opt_allow_lshift.load();
     sa.start_sel = (uint32_t)start_sel;
-    sa.guess_p1 = ha.guess_p1; sa.ghist_exact = ghist_exact;
+    sa.guess_p1 = ha.guess_p1; sa.guess_lshift = ha.guess_lshift; sa.ghist_exact = ghist_exact;
     auto launch_scan = [&]() -> int {
       {
         ProfScope ps(PK_SCAN, stream);
@@ -455,10 +491,15 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     const bool soa = streams[0].elem_bytes == (uint32_t)kb;
     const bool use_fix = have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == 1 && opt_fix_in_pass.load() != 0;
     int last_pass = -1;
+    bool first_exec = true;
+    if (landing && hplan.n_exec == 0) {  // nothing will move the records: deliver them
+      if (int rc = copy_landing_to_caller()) return rc;
+    }
     for (int p = 0; p < kb; p++) {
       if (have_plan && hplan.skip[p]) continue;
       SweepArgs wa{};
-      wa.ss = ss; wa.n = n; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
+      wa.ss = (landing && first_exec) ? ss_in : ss; wa.n = n;
+      first_exec = false; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
       wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes; wa.spin_ns = (uint32_t)opt_spin_ns.load();
@@ -543,7 +584,9 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
         // a long bucket with distinct keys: finish with the plain digit-by-digit path (the array is a
         // permutation of the input, already ordered by its top digits)
         const int64_t saved = opt_algo.exchange(1);
-        const int rc = sort_device(key_type, ascending, n, streams, stream, caller_workspace, workspace_bytes, 0, layout_n);
+        DevSortOpts fo;
+        fo.layout_n = layout_n; fo.layout_landing = xo.layout_landing;
+        const int rc = sort_device(key_type, ascending, n, streams, stream, caller_workspace, workspace_bytes, fo);
         opt_algo.store(saved);
         if (rc != 0) return rc;
         b200sort_stats s2 = g_last_stats;
@@ -733,6 +776,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "probe_guess")) return &opt_probe_guess;
   if (!strcmp(name, "allow_lshift")) return &opt_allow_lshift;
   if (!strcmp(name, "mgpu_p2p")) return &opt_mgpu_p2p;
+  if (!strcmp(name, "mgpu_landing")) return &opt_mgpu_landing;
   if (!strcmp(name, "host_plan_min_log2")) return &opt_host_plan_min_log2;
   if (!strcmp(name, "nstage")) return &opt_nstage;
   return nullptr;

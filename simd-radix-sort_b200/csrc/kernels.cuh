@@ -167,6 +167,7 @@ struct HistArgs {
   uint32_t sample_one;  // ... with one key per thread (1) or all of its keys (0)
   uint32_t with_minmax; // probe_kernel: also the smallest / largest key (else left to minmax_kernel, on demand)
   uint32_t guess_p1;    // probe_kernel: digit position + 1 whose EXACT histogram is counted on the way (0 = none)
+  uint32_t guess_lshift;  // ... of the key shifted left by this many bits (the plan's expected Plan::lshift)
   uint64_t *ghist_exact;  // [KB][RADIX] exact histograms (probe_kernel: row guess_p1 - 1)
 };
 
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
     if (exact) {
       // plain shared-memory atomics unless this warp's first row shows a crowded digit (skewed keys would
       // serialise on one counter): then equal digits are aggregated first
-      const uint32_t d0 = (uint32_t)(kt.u[0] >> gshift) & (RADIX - 1);
+      const uint32_t d0 = (uint32_t)((O)(kt.u[0] << a.guess_lshift) >> gshift) & (RADIX - 1);
       const bool full = kt.valid == (KT::PER_THREAD >= 32 ? 0xffffffffu : ((1u << KT::PER_THREAD) - 1));
       const bool crowded = !__all_sync(0xffffffffu, full) ||
                            __popc(__ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0))) >= 4;
@@ -286,11 +287,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) probe_kernel(HistArgs
         for (int i = 0; i < KT::PER_THREAD; i++) {
           const bool v = (kt.valid >> i) & 1;
           const unsigned vmask = __ballot_sync(0xffffffffu, v);
-          if (v) hist_add<true>(shx, (uint32_t)(kt.u[i] >> gshift) & (RADIX - 1), vmask);
+          if (v) hist_add<true>(shx, (uint32_t)((O)(kt.u[i] << a.guess_lshift) >> gshift) & (RADIX - 1), vmask);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < KT::PER_THREAD; i++) atomicAdd(&shx[(uint32_t)(kt.u[i] >> gshift) & (RADIX - 1)], 1u);
+        for (int i = 0; i < KT::PER_THREAD; i++) atomicAdd(&shx[(uint32_t)((O)(kt.u[i] << a.guess_lshift) >> gshift) & (RADIX - 1)], 1u);
       }
     }
     // every CTA samples every sample-th of ITS OWN tiles (tile % sample would pile all sampled tiles on
@@ -438,6 +439,7 @@ struct ScanArgs {
   int allow_lshift;        // 1: the plan may shift the keys left by their common leading bits
   uint32_t start_sel;      // side of the ping-pong that holds the input (0 = the caller's arrays)
   uint32_t guess_p1;       // digit position + 1 probe_kernel counted exactly into ghist_exact (0 = none)
+  uint32_t guess_lshift;   // ... of the key shifted left by this many bits
   uint64_t *ghist_exact;
 };
 
@@ -581,7 +583,7 @@ static __global__ void __launch_bounds__(RADIX) scan_kernel(ScanArgs a) {
     a.plan->n_exec = n_exec;
     a.plan->cut_digit = cut;
     a.plan->n_const = n_const;
-    s_hist_done = (a.guess_p1 != 0 && a.plan->first_exec_p1 == a.guess_p1 && sub == 0 && lshift == 0) ? 1u : 0u;
+    s_hist_done = (a.guess_p1 != 0 && a.plan->first_exec_p1 == a.guess_p1 && sub == 0 && lshift == a.guess_lshift) ? 1u : 0u;
     a.plan->hist_done = s_hist_done;
   }
   __syncthreads();

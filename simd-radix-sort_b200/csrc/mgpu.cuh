@@ -115,24 +115,50 @@ struct DestCountArgs {
   int shift;
   const uint8_t *lut;
   unsigned long long *counts;  // [RADIX], zeroed
+  int world;
+  const uint32_t *bounds;      // [world + 1] splitters (bin indices)
 };
 
 template <int KB, int NLD>
 __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_kernel(DestCountArgs a) {
   using KT = KeyTile<KB, HIST_THREADS, NLD>;
   __shared__ uint32_t sh[RADIX];
+  __shared__ uint32_t s_bound[32];  // upper bin boundary of rank r (exclusive)
   for (int i = threadIdx.x; i < RADIX; i += HIST_THREADS) sh[i] = 0;
+  if (threadIdx.x < 32) s_bound[threadIdx.x] = (int)threadIdx.x < a.world ? a.bounds[threadIdx.x + 1] : 0u;
   __syncthreads();
   const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
+  uint32_t lane_cnt = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
     kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);
+    if (a.world <= 32) {
+      // few destinations: no table look-up (a random byte load per key is what would bound this kernel).
+      // Lane r counts the keys below the upper boundary of rank r: one compare + ballot per rank and row;
+      // the counts per destination are the differences.
 #pragma unroll
-    for (int i = 0; i < KT::PER_THREAD; i++) {
-      const bool v = (kt.valid >> i) & 1;
-      const unsigned vmask = __ballot_sync(0xffffffffu, v);
-      if (v) hist_add<true>(sh, (uint32_t)a.lut[(uint32_t)(kt.u[i] >> a.shift)], vmask);  // few destinations: aggregate
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const bool v = (kt.valid >> i) & 1;
+        const uint32_t bin = v ? (uint32_t)(kt.u[i] >> a.shift) : 0xffffffffu;
+        for (int r = 0; r < a.world; r++) {
+          const unsigned bal = __ballot_sync(0xffffffffu, bin < s_bound[r]);
+          if ((int)(threadIdx.x & 31) == r) lane_cnt += __popc(bal);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const bool v = (kt.valid >> i) & 1;
+        const unsigned vmask = __ballot_sync(0xffffffffu, v);
+        if (v) hist_add<true>(sh, (uint32_t)a.lut[(uint32_t)(kt.u[i] >> a.shift)], vmask);
+      }
     }
+  }
+  if (a.world <= 32) {
+    // lane r holds #keys below bound r+1 (cumulative): difference with the lane before gives rank r's count
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, lane_cnt, 1);
+    const uint32_t mine = lane_cnt - ((threadIdx.x & 31) ? prev : 0u);
+    if ((int)(threadIdx.x & 31) < a.world && mine) atomicAdd(&sh[threadIdx.x & 31], mine);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RADIX; i += HIST_THREADS) {
@@ -210,6 +236,7 @@ struct b200sort_comm {
   unsigned long long *d_hist = nullptr;   // [2^16] local, then reduced in place
   unsigned long long *d_counts = nullptr; // [world] send counts, [world*world] gathered (NCCL path scratch, barrier word)
   uint8_t *d_lut = nullptr;               // [2^16]
+  uint32_t *d_bounds = nullptr;           // [RADIX + 1] splitters
   uint64_t *d_bin_base = nullptr;         // [RADIX]
   int64_t *d_peer_delta = nullptr;        // [RADIX]
   MgpuBlob *d_blob = nullptr;             // [world]
@@ -290,6 +317,7 @@ int b200sort_mgpu_comm_create(b200sort_comm **out, int world_size, int rank, con
   CUDA_TRY(cudaMalloc(&c->d_bin_base, sizeof(uint64_t) * RADIX));
   CUDA_TRY(cudaMalloc(&c->d_plan, sizeof(Plan)));
   CUDA_TRY(cudaMalloc(&c->d_peer_delta, sizeof(int64_t) * RADIX));
+  CUDA_TRY(cudaMalloc(&c->d_bounds, sizeof(uint32_t) * (RADIX + 1)));
   CUDA_TRY(cudaMalloc(&c->d_blob, sizeof(MgpuBlob) * (size_t)world_size));
   c->peer_handle.resize(world_size);
   c->peer_base.assign(world_size, nullptr);
@@ -305,7 +333,7 @@ int b200sort_mgpu_comm_destroy(b200sort_comm *c) {
   for (int p = 0; p < c->world; p++)
     if (p != c->rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
   cudaFree(c->d_hist); cudaFree(c->d_counts); cudaFree(c->d_lut); cudaFree(c->d_bin_base); cudaFree(c->d_plan);
-  cudaFree(c->d_peer_delta); cudaFree(c->d_blob);
+  cudaFree(c->d_peer_delta); cudaFree(c->d_blob); cudaFree(c->d_bounds);
   delete c;
   return 0;
 }
@@ -371,8 +399,13 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   const TileCfg tc = kTileCfgs[cfg];
   const int tile = tc.threads * tc.ipt;
   const int64_t n_ws = std::max<int64_t>(capacity, 1);
+  // Large 8-byte-key sorts receive into a third set of arrays (landing): the local sort then runs
+  // landing -> shadow -> caller -> shadow -> caller and an even number of passes ends in the caller's arrays
+  // without a copy.  The choice depends on nothing but the arguments all ranks share.
+  const bool landing = kb == 8 && n_ws >= ((int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62)) &&
+                       opt_mgpu_landing.load() != 0 && opt_mgpu_p2p.load() != 0;
   Layout L;
-  make_layout(streams, n_ws, std::min(tile, HYB_MIN_TILE), &L);
+  make_layout(streams, n_ws, std::min(tile, HYB_MIN_TILE), &L, landing);
   void *ws_v = nullptr;
   if (int rc = cached_workspace(c->dev, L.total, &ws_v)) return rc;
   unsigned char *ws = (unsigned char *)ws_v;
@@ -398,6 +431,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   for (int r = 0; r < world; r++)
     for (uint32_t b = bounds[r]; b < bounds[r + 1]; b++) lut[b] = (uint8_t)r;
   CUDA_TRY(cudaMemcpyAsync(c->d_lut, lut.data(), nb, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_bounds, bounds.data(), sizeof(uint32_t) * (world + 1), cudaMemcpyHostToDevice, stream));
 
   // 3: my blob = {workspace handle, layout size, capacity, exact send counts}; all-gather
   MgpuBlob mine{};
@@ -412,7 +446,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   MgpuBlob *my_slot = c->d_blob + c->rank;
   CUDA_TRY(cudaMemcpyAsync(my_slot, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));  // counts zeroed with it
   if (num_local > 0) {
-    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts};
+    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts, world, c->d_bounds};
     CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
   }
   NCCL_TRY(api.AllGather(my_slot, c->d_blob, sizeof(MgpuBlob), ncclUint8, c->comm, stream));
@@ -496,6 +530,8 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
     if (num_local > 0) {
       SweepArgs wa{};
       wa.ss = ss; wa.n = num_local; wa.ko = ko; wa.pass = 0; wa.shift = 0;
+      if (p2p && landing)
+        for (size_t s2 = 0; s2 < streams.size(); s2++) wa.ss.streams[s2].buf[1] = ws + L.land_off[s2];
       wa.bin_base = c->d_bin_base; wa.lookback = (uint64_t *)(ws + L.lookback_off);
       wa.tile_counter = (uint32_t *)(ws + L.tilectr_off); wa.plan = c->d_plan; wa.tag = 1; wa.stage_bytes = stage_bytes;
       wa.lut = c->d_lut; wa.lut_shift = shift;
@@ -516,7 +552,19 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
     trace.mark("barrier");
     // 5: local sort, input in the shadow arrays, result in the caller's arrays
     if (recv_total > 0) {
-      int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0, /*start_sel=*/1, /*layout_n=*/n_ws);
+      // leading key bits this rank's range [bounds[rank], bounds[rank+1]) of top-`bits` values has in common
+      int lead = 0;
+      if (kb == 8 && bounds[c->rank + 1] > bounds[c->rank]) {
+        const uint32_t x = bounds[c->rank] ^ (bounds[c->rank + 1] - 1);
+        lead = x ? __builtin_clz(x) - (32 - bits) : bits;
+      }
+      DevSortOpts so;
+      so.start_sel = landing ? 0 : 1;
+      so.layout_n = n_ws;
+      so.hint_lead_bits = lead;
+      so.layout_landing = landing;
+      so.landing_input = landing;
+      int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0, so);
       if (rc != 0) return rc;
     }
   } else {
@@ -533,7 +581,10 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
     NCCL_TRY(api.GroupEnd());
     trace.mark("exchange");
     if (recv_total > 1) {
-      int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0);
+      DevSortOpts so;
+      so.layout_n = n_ws;
+      so.layout_landing = landing;
+      int rc = sort_device(key_type, ascending != 0, recv_total, streams, stream, nullptr, 0, so);
       if (rc != 0) return rc;
     }
   }

@@ -35,8 +35,12 @@ def main():
     cases = [(np.uint64, "Uniform", True, 1_000_003), (np.float32, "Gaussian", False, 400_000), (np.int16, "Uniform", True, 250_000),
              (np.int64, "Gaussian", True, 300_000), (np.float64, "Uniform", False, 2_000_000)]
     L.b200sort_mgpu_used_p2p.argtypes = [ctypes.c_void_p]
-    for p2p in (1, 0):  # records scattered straight into peer memory / exchanged with ncclSend+ncclRecv
+    # records scattered straight into peer memory (twice: with the large-sort flow forced, whose local sort
+    # reads the landing arrays in its first pass) / exchanged with ncclSend+ncclRecv
+    for p2p, big_flow in ((1, 1), (1, 0), (0, 0)):
         S.set_option("mgpu_p2p", p2p)
+        S.set_option("host_plan_min_log2", 0 if big_flow else 24)
+        S.set_option("algo", 2 if big_flow else 0)
         for ci, (dt, distname, up, n_base) in enumerate(cases):
             n_local = n_base + 1000 * rank
             keys = O.make_keys(distname, dt, n_local, seed=100 * ci + rank)
@@ -72,17 +76,19 @@ def main():
                 all_out_p = np.concatenate([g[3] for g in gathered])
                 all_out_p2 = np.concatenate([g[4] for g in gathered])
                 want = O.total_order_sorted_keys(all_in_k, up)
-                assert all_out_k.tobytes() == want.tobytes(), f"case {ci} p2p={p2p}: distributed key sequence differs"
+                assert all_out_k.tobytes() == want.tobytes(), f"case {ci} p2p={p2p} big={big_flow}: distributed key sequence differs"
                 # payload followed its key: payload encodes (source rank, source index)
                 src_rank, src_idx = all_out_p >> np.uint64(40), all_out_p & np.uint64((1 << 40) - 1)
                 offs = np.cumsum([0] + [len(g[0]) for g in gathered])[:-1]
                 pos = offs[src_rank.astype(np.int64)] + src_idx.astype(np.int64)
-                assert all_in_k[pos].tobytes() == all_out_k.tobytes(), f"case {ci} p2p={p2p}: payload did not follow its key"
-                assert np.array_equal(np.sort(pos), np.arange(len(all_in_k))), f"case {ci} p2p={p2p}: not a permutation"
-                assert np.array_equal(all_out_p2, (src_idx % np.uint64(65521)).astype(np.uint16)), f"case {ci} p2p={p2p}: second payload"
+                assert all_in_k[pos].tobytes() == all_out_k.tobytes(), f"case {ci} p2p={p2p} big={big_flow}: payload did not follow its key"
+                assert np.array_equal(np.sort(pos), np.arange(len(all_in_k))), f"case {ci} p2p={p2p} big={big_flow}: not a permutation"
+                assert np.array_equal(all_out_p2, (src_idx % np.uint64(65521)).astype(np.uint16)), f"case {ci} p2p={p2p} big={big_flow}: second payload"
                 sizes_out = [len(g[2]) for g in gathered]
                 assert max(sizes_out) <= 1.3 * (sum(sizes_out) / world) + 70000, f"case {ci}: unbalanced {sizes_out}"
     S.set_option("mgpu_p2p", 1)
+    S.set_option("host_plan_min_log2", 24)
+    S.set_option("algo", 0)
     dist.barrier()
     assert L.b200sort_mgpu_comm_destroy(comm) == 0
     dist.destroy_process_group()
