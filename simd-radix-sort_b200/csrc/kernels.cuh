@@ -1066,7 +1066,13 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           members &= members - 1;
           const int i = base + sl;
           const KeyT kraw = key_at(i);
-          const O ok = to_ordered<KB>(kraw, ko);
+          // All members of a run share the swept bits, the sign among them: the order mapping xors them with
+          // one and the same constant, whose bits below the cut are all zeros or all ones (no range reduction
+          // here, and a left shift keeps the order).  So the full-key order inside the run is the order of the
+          // raw keys, reversed if that constant's low bits are ones: compare raw keys xor-ed with 0 or ~0.
+          const O sgn = (O)0 - (((O)kraw >> (8 * KB - 1)) & 1);
+          const O flip = (O)0 - (((O)ko.xor_const ^ (sgn & (O)ko.neg_xor)) & 1);
+          const O ok = (O)kraw ^ flip;
           // neighbours known to be in the run from the window bits, then (rarely) beyond the window
           const uint32_t below = ~eq & ((2u << sl) - 1u);  // zero bits at or below sl stop the run on the left
           int nl = below ? sl - (31 - __clz(below)) : sl + 1;
@@ -1087,10 +1093,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
             // Too long to be ordered here: every member keeps its slot and checks its own (slot, slot+1) pair;
             // if none is out of order the run is in order as it stands (duplicates of one key, typically)
             // and nobody has to be told.
-            if (((eq >> (sl + 1)) & 1u) && to_ordered<KB>(key_at(i + 1), ko) < ok && ld_relaxed_u32(a.fix_flag) == 0) atomicOr(a.fix_flag, 1u);
+            if (((eq >> (sl + 1)) & 1u) && ((O)key_at(i + 1) ^ flip) < ok && ld_relaxed_u32(a.fix_flag) == 0) atomicOr(a.fix_flag, 1u);
           } else {
-            for (int q = 1; q <= nl; q++) cl += to_ordered<KB>(key_at(i - q), ko) > ok;
-            for (int q = 1; q <= nr; q++) cr += to_ordered<KB>(key_at(i + q), ko) < ok;
+            for (int q = 1; q <= nl; q++) cl += ((O)key_at(i - q) ^ flip) > ok;
+            for (int q = 1; q <= nr; q++) cr += ((O)key_at(i + q) ^ flip) < ok;
           }
           if (cr != cl) sdelta[i] = (int8_t)(cr - cl);
         }
