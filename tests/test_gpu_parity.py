@@ -420,3 +420,35 @@ def test_hybrid_left_shift_plan_for_common_leading_bits(host_plan):
         S.set_option("allow_lshift", 1)
         S.set_option("host_plan_min_log2", 24)
         S.set_option("margin_bits", 2)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_arrays_pipelined_staging(pinned):
+    """host SoA arrays, >= 2^20 records: keys are sorted with an index while the payloads upload, payloads are
+    permuted afterwards (pageable and pinned host memory take different issue orders)"""
+    n = (1 << 20) + 12345
+    rng = np.random.default_rng(31)
+    for dt, up in ((np.uint64, True), (np.float32, False), (np.int16, True)):
+        keys = O.make_keys("Uniform", dt, n, seed=3)
+        pays = [np.arange(n, dtype=np.uint64), (np.arange(n) % 65521).astype(np.uint16),
+                rng.integers(0, 255, size=(n, 12), dtype=np.uint8)]  # 8-, 2- and 12-byte payload elements
+        if pinned:
+            tk = torch.from_numpy(keys.copy()).pin_memory()
+            tp = [torch.from_numpy(p.copy()).pin_memory() for p in pays]
+            k, ps = tk.numpy(), [t.numpy() for t in tp]
+        else:
+            k, ps = keys.copy(), [p.copy() for p in pays]
+        before = S.launch_count()
+        L = S.lib()
+        import ctypes
+        ptrs = (ctypes.c_void_p * 3)(*[p.ctypes.data for p in ps])
+        sizes = (ctypes.c_uint32 * 3)(8, 2, 12)
+        rc = L.b200sort_sort_soa(ctypes.c_void_p(k.ctypes.data), S.KEY_TYPES[np.dtype(dt).name], n, int(up), 3, ptrs, sizes, None, None, 0)
+        assert rc == 0, L.b200sort_last_error()
+        assert S.launch_count() > before
+        want = O.total_order_sorted_keys(keys, up)
+        assert k.tobytes() == want.tobytes(), (dt, up, pinned)
+        src = ps[0].astype(np.int64)
+        assert np.array_equal(np.sort(src), np.arange(n)) and keys[src].tobytes() == k.tobytes()
+        assert np.array_equal(ps[1], (src % 65521).astype(np.uint16))
+        assert np.array_equal(ps[2], pays[2][src])
