@@ -53,6 +53,14 @@ __device__ __forceinline__ typename OrdOf<KB>::type to_ordered(typename UIntOf<K
   return SHIFT ? (O)(v << ko.lshift) : v;  // SHIFT = false: callers that know lshift == 0 (the probe)
 }
 
+// multi-GPU: histogram bin of an ordered key inside the (sampled) global key range [lo, lo + (nb << shift)):
+// keys outside the sampled range fall into the first / last bin, which keeps the mapping monotonic
+__device__ __forceinline__ uint32_t range_bin(unsigned long long u, unsigned long long lo, int shift, uint32_t nb) {
+  if (u <= lo) return 0u;
+  const unsigned long long b = (u - lo) >> shift;
+  return b >= nb ? nb - 1u : (uint32_t)b;
+}
+
 template <int KB>
 __device__ __forceinline__ typename UIntOf<KB>::type load_key(const unsigned char *base, int64_t i, uint32_t stride) {
   return *reinterpret_cast<const typename UIntOf<KB>::type *>(base + (size_t)i * stride);
@@ -618,6 +626,8 @@ struct SweepArgs {
   // top lut_bits bits of the ordered key (lut has 2^lut_bits entries), not a radix digit
   const uint8_t *lut;
   int lut_shift;
+  unsigned long long lut_lo;  // bin = range_bin(ordered key, lut_lo, lut_shift, lut_bins)
+  uint32_t lut_bins;
   // ... and bucket d is written at byte offset peer_delta[d] from this GPU's own destination arrays: the
   // same array in the workspace of GPU d, mapped into this process (nullptr: everything stays local)
   const int64_t *peer_delta;
@@ -671,7 +681,7 @@ __device__ __forceinline__ uint32_t fast_digit(typename UIntOf<KB>::type raw, co
 
 template <int KB>
 __device__ __forceinline__ uint32_t lut_digit(typename UIntOf<KB>::type raw, const SweepArgs &a) {
-  return a.lut[(uint32_t)(to_ordered<KB>(raw, a.ko) >> a.lut_shift)];
+  return a.lut[range_bin((unsigned long long)to_ordered<KB>(raw, a.ko), a.lut_lo, a.lut_shift, a.lut_bins)];
 }
 
 // ---- staging of one chunk column of one stream ---------------------------------------------------------
@@ -796,7 +806,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         uint32_t w = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++)
-          w |= pad(4 * q + e, a.lut[(uint32_t)(to_ordered<KB>(raw[4 * q + e], ko) >> a.lut_shift)]) << (8 * e);  // partition pass
+          w |= pad(4 * q + e, a.lut[range_bin((unsigned long long)to_ordered<KB>(raw[4 * q + e], ko), a.lut_lo, a.lut_shift, a.lut_bins)]) << (8 * e);  // partition pass
         dpack[q] = w;
       }
     } else if (has_sub) {

@@ -68,9 +68,12 @@ struct TopHistArgs {
   uint32_t stride;
   int64_t n;
   KeyOrder ko;
-  int shift;            // ordered key >> shift = bin
-  unsigned long long *hist;  // [2^bits], zeroed
+  int shift;            // bin = range_bin(ordered key, lo, shift, nb)
+  unsigned long long *hist;  // [nb], zeroed
   int64_t sample;       // every sample-th row of 32 keys is counted
+  unsigned long long lo;
+  uint32_t nb;
+  unsigned long long *range;  // range_kernel: [0] = min ordered key, [1] = min of the complements (= ~max)
 };
 
 template <int KB>
@@ -85,22 +88,59 @@ __global__ void __launch_bounds__(256) top_hist_kernel(TopHistArgs a) {
     const bool valid = i < a.n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     if (valid) {
-      const uint32_t bin = (uint32_t)(to_ordered<KB, false>(load_key<KB>(a.keys, i, a.stride), a.ko) >> a.shift);
+      const uint32_t bin = range_bin((unsigned long long)to_ordered<KB, false>(load_key<KB>(a.keys, i, a.stride), a.ko), a.lo, a.shift, a.nb);
       const unsigned peers = __match_any_sync(vmask, bin);
       if ((peers & lanemask_lt()) == 0) atomicAdd(&a.hist[bin], (unsigned long long)__popc(peers));
     }
   }
 }
 
-static cudaError_t launch_top_hist(int kb, const TopHistArgs &a, int sm_count, cudaStream_t st) {
+// smallest and largest ordered key of the same sample: the histogram bins cover that range, not the whole key
+// space (keys of a narrow range -- small integers, N(0,1) doubles -- would otherwise share one or two bins)
+template <int KB>
+__global__ void __launch_bounds__(256) range_kernel(TopHistArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_rows = (a.n + 31) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x / 32);
+  unsigned long long mn = ~0ull, nmx = ~0ull;
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * a.sample < n_rows; w += n_warps) {
+    const int64_t i = w * a.sample * 32 + lane;
+    if (i < a.n) {
+      const unsigned long long u = (unsigned long long)to_ordered<KB, false>(load_key<KB>(a.keys, i, a.stride), a.ko);
+      mn = u < mn ? u : mn;
+      nmx = ~u < nmx ? ~u : nmx;
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mn, s), n2 = __shfl_xor_sync(0xffffffffu, nmx, s);
+    mn = m2 < mn ? m2 : mn;
+    nmx = n2 < nmx ? n2 : nmx;
+  }
+  if (lane == 0) {
+    atomicMin(&a.range[0], mn);
+    atomicMin(&a.range[1], nmx);
+  }
+}
+
+static cudaError_t launch_top_hist(int kb, const TopHistArgs &a, int sm_count, cudaStream_t st, bool range_only = false) {
   const int64_t rows = ((a.n + 31) / 32 + a.sample - 1) / a.sample;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count * 16));
   ProfScope ps(PK_HIST, st);
-  switch (kb) {
-    case 1: top_hist_kernel<1><<<grid, 256, 0, st>>>(a); break;
-    case 2: top_hist_kernel<2><<<grid, 256, 0, st>>>(a); break;
-    case 4: top_hist_kernel<4><<<grid, 256, 0, st>>>(a); break;
-    default: top_hist_kernel<8><<<grid, 256, 0, st>>>(a); break;
+  if (range_only) {
+    switch (kb) {
+      case 1: range_kernel<1><<<grid, 256, 0, st>>>(a); break;
+      case 2: range_kernel<2><<<grid, 256, 0, st>>>(a); break;
+      case 4: range_kernel<4><<<grid, 256, 0, st>>>(a); break;
+      default: range_kernel<8><<<grid, 256, 0, st>>>(a); break;
+    }
+  } else {
+    switch (kb) {
+      case 1: top_hist_kernel<1><<<grid, 256, 0, st>>>(a); break;
+      case 2: top_hist_kernel<2><<<grid, 256, 0, st>>>(a); break;
+      case 4: top_hist_kernel<4><<<grid, 256, 0, st>>>(a); break;
+      default: top_hist_kernel<8><<<grid, 256, 0, st>>>(a); break;
+    }
   }
   g_launches++;
   return cudaGetLastError();
@@ -117,6 +157,8 @@ struct DestCountArgs {
   unsigned long long *counts;  // [RADIX], zeroed
   int world;
   const uint32_t *bounds;      // [world + 1] splitters (bin indices)
+  unsigned long long lo;       // bin = range_bin(ordered key, lo, shift, nb)
+  uint32_t nb;
 };
 
 template <int KB, int NLD>
@@ -139,7 +181,7 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
 #pragma unroll
       for (int i = 0; i < KT::PER_THREAD; i++) {
         const bool v = (kt.valid >> i) & 1;
-        const uint32_t bin = v ? (uint32_t)(kt.u[i] >> a.shift) : 0xffffffffu;
+        const uint32_t bin = v ? range_bin((unsigned long long)kt.u[i], a.lo, a.shift, a.nb) : 0xffffffffu;
         for (int r = 0; r < a.world; r++) {
           const unsigned bal = __ballot_sync(0xffffffffu, bin < s_bound[r]);
           if ((int)(threadIdx.x & 31) == r) lane_cnt += __popc(bal);
@@ -150,7 +192,7 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
       for (int i = 0; i < KT::PER_THREAD; i++) {
         const bool v = (kt.valid >> i) & 1;
         const unsigned vmask = __ballot_sync(0xffffffffu, v);
-        if (v) hist_add<true>(sh, (uint32_t)a.lut[(uint32_t)(kt.u[i] >> a.shift)], vmask);
+        if (v) hist_add<true>(sh, (uint32_t)a.lut[range_bin((unsigned long long)kt.u[i], a.lo, a.shift, a.nb)], vmask);
       }
     }
   }
@@ -377,7 +419,6 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   const int world = c->world;
   const int bits = std::min(MGPU_MAX_BITS, 8 * kb);
   const uint32_t nb = 1u << bits;
-  const int shift = 8 * kb - bits;
   DevInfo di;
   if (int rc = dev_info(c->dev, &di)) return rc;
   const KeyOrder ko = make_key_order(key_type, ascending != 0);
@@ -411,13 +452,30 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   unsigned char *ws = (unsigned char *)ws_v;
   for (size_t s = 0; s < streams.size(); s++) ss.streams[s].buf[1] = ws + L.shadow_off[s];
 
-  // 1-2: histogram of the top bits of a sample of the local keys, all-reduce
+  // 1: key range of a sample of all ranks' keys (min / max all-reduced), then the histogram of that range in
+  //    2^bits bins on the same sample, all-reduced
+  const int64_t sample = std::max<int64_t>(1, num_local >> 24);  // about 2^24 sampled keys at most
+  unsigned long long range_h[2] = {~0ull, ~0ull};
+  CUDA_TRY(cudaMemcpyAsync(c->d_counts, range_h, sizeof range_h, cudaMemcpyHostToDevice, stream));
+  TopHistArgs ha{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, 0, c->d_hist, sample, 0ull, nb, c->d_counts};
+  if (num_local > 0) CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream, /*range_only=*/true));
+  NCCL_TRY(api.AllReduce(c->d_counts, c->d_counts, 2, ncclUint64, ncclMin, c->comm, stream));
+  CUDA_TRY(cudaMemcpyAsync(range_h, c->d_counts, sizeof range_h, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned long long) * nb, stream));
-  if (num_local > 0) {
-    TopHistArgs ha{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_hist,
-                   std::max<int64_t>(1, num_local >> 24)};  // about 2^24 sampled keys at most
-    CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  unsigned long long lo = range_h[0], hi = ~range_h[1];
+  if (lo > hi) lo = hi = 0;  // no keys anywhere
+  int shift = 0;
+  {
+    const unsigned long long span = hi - lo;
+    const int span_bits = span ? 64 - __builtin_clzll(span) : 0;
+    shift = std::max(0, span_bits - bits);
+    // full-width keys: keep the bins aligned with the key's own leading bits (the local sorts then see shards
+    // with constant leading bits and can shift them out)
+    if (span_bits > 8 * kb - 2) { lo = 0; shift = 8 * kb - bits; }
   }
+  ha.lo = lo; ha.shift = shift;
+  if (num_local > 0) CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream));
   std::vector<uint64_t> global_hist(nb);
   NCCL_TRY(api.AllReduce(c->d_hist, c->d_hist, nb, ncclUint64, ncclSum, c->comm, stream));
   CUDA_TRY(cudaMemcpyAsync(global_hist.data(), c->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, stream));
@@ -446,7 +504,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   MgpuBlob *my_slot = c->d_blob + c->rank;
   CUDA_TRY(cudaMemcpyAsync(my_slot, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));  // counts zeroed with it
   if (num_local > 0) {
-    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts, world, c->d_bounds};
+    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts, world, c->d_bounds, lo, nb};
     CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
   }
   NCCL_TRY(api.AllGather(my_slot, c->d_blob, sizeof(MgpuBlob), ncclUint8, c->comm, stream));
@@ -534,7 +592,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
         for (size_t s2 = 0; s2 < streams.size(); s2++) wa.ss.streams[s2].buf[1] = ws + L.land_off[s2];
       wa.bin_base = c->d_bin_base; wa.lookback = (uint64_t *)(ws + L.lookback_off);
       wa.tile_counter = (uint32_t *)(ws + L.tilectr_off); wa.plan = c->d_plan; wa.tag = 1; wa.stage_bytes = stage_bytes;
-      wa.lut = c->d_lut; wa.lut_shift = shift;
+      wa.lut = c->d_lut; wa.lut_shift = shift; wa.lut_lo = lo; wa.lut_bins = nb;
       wa.peer_delta = p2p ? c->d_peer_delta : nullptr;
       CUDA_TRY(launch_sweep(kb, cfg, wa, (num_local + tile - 1) / tile, di.smem_optin, di.sm_count, stream));
     }
@@ -554,7 +612,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
     if (recv_total > 0) {
       // leading key bits this rank's range [bounds[rank], bounds[rank+1]) of top-`bits` values has in common
       int lead = 0;
-      if (kb == 8 && bounds[c->rank + 1] > bounds[c->rank]) {
+      if (kb == 8 && lo == 0 && shift == 8 * kb - bits && bounds[c->rank + 1] > bounds[c->rank]) {
         const uint32_t x = bounds[c->rank] ^ (bounds[c->rank + 1] - 1);
         lead = x ? __builtin_clz(x) - (32 - bits) : bits;
       }
