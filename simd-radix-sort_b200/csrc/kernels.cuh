@@ -628,6 +628,7 @@ struct SweepArgs {
   int lut_shift;
   unsigned long long lut_lo;  // bin = range_bin(ordered key, lut_lo, lut_shift, lut_bins)
   uint32_t lut_bins;
+  int lut_world;              // number of destinations (buckets in use)
   // ... and bucket d is written at byte offset peer_delta[d] from this GPU's own destination arrays: the
   // same array in the workspace of GPU d, mapped into this process (nullptr: everything stays local)
   const int64_t *peer_delta;
@@ -731,18 +732,25 @@ __device__ __forceinline__ void stage_sync(const unsigned char *src, unsigned ch
 // shared by all streams): consecutive threads write consecutive addresses of each bucket.
 template <typename T, int THREADS, int IPT, bool FULL, bool PEER = false>
 __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const int64_t (&goff)[IPT], int n_valid,
-                                          uint32_t cpe, uint32_t c, const uint8_t *sdigit = nullptr, const int64_t *pdelta = nullptr) {
+                                          uint32_t cpe, uint32_t c, const int64_t *pdelta = nullptr, const uint32_t *s_prefix = nullptr,
+                                          const int64_t *gbase = nullptr, int n_buckets = 0) {
   const T *stage = reinterpret_cast<const T *>(buf) + threadIdx.x;
   T *d = reinterpret_cast<T *>(dst) + c;
   if constexpr (PEER) {
-    // partition pass of the multi-GPU sort: the bucket is a destination GPU, its arrays are peer memory
-#pragma unroll
-    for (int k = 0; k < IPT; k++) {
-      const int i = (int)threadIdx.x + k * THREADS;
-      if (FULL || i < n_valid) {
-        T *dp = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(d) + pdelta[sdigit[i]]);
-        dp[(size_t)goff[k] * cpe] = stage[k * THREADS];
-      }
+    // Partition pass of the multi-GPU sort: a bucket is a destination GPU, its arrays are peer memory.
+    // Bucket by bucket, with the threads aligned to the DESTINATION: every warp store then covers one
+    // naturally aligned 32-element block of the peer's array (256 B of 8-byte elements), which is what
+    // NVLink moves best; only the first and last block of a bucket's run are partial.
+    for (int b = 0; b < n_buckets; b++) {
+      const int s0 = (int)s_prefix[b];
+      const int s1 = b + 1 < RADIX ? (int)s_prefix[b + 1] : n_valid;
+      const int cnt = min(s1, n_valid) - s0;
+      if (cnt <= 0) continue;
+      const int64_t g0 = gbase[b] + s0;  // destination index of the bucket's first staged slot
+      T *dp = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(d) + pdelta[b]);
+      const T *sp = reinterpret_cast<const T *>(buf);
+      for (int e = (int)threadIdx.x - (int)(g0 & 31); e < cnt; e += THREADS)
+        if (e >= 0) dp[(size_t)(g0 + e) * cpe] = sp[s0 + e];
     }
   } else if (cpe == 1) {  // one chunk per element (the common shapes): no index multiply
 #pragma unroll
@@ -1129,11 +1137,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       unsigned char *dst = st.buf[sel ^ 1];
       const unsigned char *buf = bufs[NSTAGE == 2 ? (j & 1) : 0];
       const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
-      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
-      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
-      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
-      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
-      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, sdigit, pdelta);
+      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
+      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
+      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
+      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
+      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
       if (++wr_c == cpe) { wr_c = 0; wr_s++; }
     }
     if (wr_s >= a.ss.n_streams) break;

@@ -507,11 +507,12 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
     DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts, world, c->d_bounds, lo, nb};
     CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
   }
+  trace.mark("count");
   NCCL_TRY(api.AllGather(my_slot, c->d_blob, sizeof(MgpuBlob), ncclUint8, c->comm, stream));
   std::vector<MgpuBlob> blobs(world);
   CUDA_TRY(cudaMemcpyAsync(blobs.data(), c->d_blob, sizeof(MgpuBlob) * world, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
-  trace.mark("count+allgather");
+  trace.mark("allgather");
 
   auto m = [&](int src, int dst) -> uint64_t { return blobs[src].counts[dst]; };
   std::vector<uint64_t> send(world);
@@ -592,7 +593,7 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
         for (size_t s2 = 0; s2 < streams.size(); s2++) wa.ss.streams[s2].buf[1] = ws + L.land_off[s2];
       wa.bin_base = c->d_bin_base; wa.lookback = (uint64_t *)(ws + L.lookback_off);
       wa.tile_counter = (uint32_t *)(ws + L.tilectr_off); wa.plan = c->d_plan; wa.tag = 1; wa.stage_bytes = stage_bytes;
-      wa.lut = c->d_lut; wa.lut_shift = shift; wa.lut_lo = lo; wa.lut_bins = nb;
+      wa.lut = c->d_lut; wa.lut_shift = shift; wa.lut_lo = lo; wa.lut_bins = nb; wa.lut_world = world;
       wa.peer_delta = p2p ? c->d_peer_delta : nullptr;
       CUDA_TRY(launch_sweep(kb, cfg, wa, (num_local + tile - 1) / tile, di.smem_optin, di.sm_count, stream));
     }
