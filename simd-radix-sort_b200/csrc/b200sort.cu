@@ -46,6 +46,7 @@ static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 static std::atomic<int64_t> opt_probe_guess{1};
 static std::atomic<int64_t> opt_allow_lshift{1};
+static std::atomic<int64_t> opt_junction_table{1};  // junction kernel compares fingerprints left by the last pass
 static std::atomic<int64_t> opt_host_pipeline{1};  // host SoA arrays: sort keys + index while the payloads upload
 static std::atomic<int64_t> opt_mgpu_landing{1};  // multi-GPU: receive into a third set of arrays (saves the final copy)
 static std::atomic<int64_t> opt_mgpu_p2p{1};  // multi-GPU: scatter straight into peer memory (0: NCCL send/recv)
@@ -252,7 +253,7 @@ struct Layout {
   size_t shadow_off[MAX_STREAMS];
   size_t land_off[MAX_STREAMS];
   size_t ctrl_off, ctrl_bytes;       // zeroed at the start of every sort
-  size_t ghist_off, ghist2_off, probe_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off;
+  size_t ghist_off, ghist2_off, probe_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off, jtable_off;
   size_t total;
   int64_t n_tiles;
 };
@@ -283,6 +284,7 @@ static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int t
   L->lookback_off = off;            off += (size_t)L->n_tiles * RADIX * 8;
   L->ctrl_bytes = off - L->ctrl_off;
   L->binbase_off = off;             off += (size_t)MAX_PASSES * RADIX * 8;
+  L->jtable_off = off;              off += (size_t)L->n_tiles * RADIX * 8;   // FIX pass -> junction_fix_kernel
   off = align_up(off, 256);
   // multi-GPU: a third copy of every stream, where the peers deliver this rank's records (see mgpu.cuh)
   for (size_t s = 0; s < streams.size(); s++) {
@@ -507,7 +509,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       if (have_plan) {
         wa.plan_in_args = 1; wa.arg_sel = hplan.src_sel[p]; wa.arg_next_p1 = hplan.next_exec_p1[p];
         wa.arg_next_skewed = hplan.next_exec_p1[p] ? hplan.skewed[hplan.next_exec_p1[p] - 1] : 0; wa.arg_sub = hplan.sub; wa.arg_lshift = hplan.lshift;
-        if (use_fix && hplan.next_exec_p1[p] == 0) { wa.fix_cut = hplan.cut_digit; wa.fix_flag = &ctrl->flags[1]; last_pass = p; }
+        if (use_fix && hplan.next_exec_p1[p] == 0) { wa.fix_cut = hplan.cut_digit; wa.fix_flag = &ctrl->flags[1]; wa.jtable = (uint64_t *)(ws + L.jtable_off); last_pass = p; }
       }
       CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream));
     }
@@ -543,6 +545,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       JunctionArgs ja{};
       ja.ss = ss; ja.n = n; ja.ko = ko; ja.ko.sub = hplan.sub; ja.ko.lshift = hplan.lshift; ja.lookback = lookback; ja.n_tiles = n_tiles;
       ja.tag = (uint32_t)(last_pass + 1); ja.cut = hplan.cut_digit; ja.sel = hplan.final_sel; ja.flag = &ctrl->flags[1];
+      ja.jtable = opt_junction_table.load() != 0 ? (const uint64_t *)(ws + L.jtable_off) : nullptr;
       const int64_t threads = n_tiles * RADIX;
       {
         ProfScope ps(PK_SEGFIX, stream);
@@ -961,6 +964,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "mgpu_p2p")) return &opt_mgpu_p2p;
   if (!strcmp(name, "mgpu_landing")) return &opt_mgpu_landing;
   if (!strcmp(name, "host_pipeline")) return &opt_host_pipeline;
+  if (!strcmp(name, "junction_table")) return &opt_junction_table;
   if (!strcmp(name, "host_plan_min_log2")) return &opt_host_plan_min_log2;
   if (!strcmp(name, "nstage")) return &opt_nstage;
   return nullptr;

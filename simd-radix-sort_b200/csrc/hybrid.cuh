@@ -228,6 +228,7 @@ struct JunctionArgs {
   uint32_t tag;              // generation tag of that pass
   uint32_t cut, sel;         // Plan::cut_digit, side holding the data
   uint32_t *flag;            // raised when a segment is too long for this kernel
+  const uint64_t *jtable;    // [n_tiles][RADIX] fingerprints written by the FIX pass (SweepArgs::jtable), or nullptr
 };
 
 template <typename T>
@@ -273,10 +274,23 @@ __global__ void __launch_bounds__(256) junction_fix_kernel(const __grid_constant
       const int64_t g_end = (int64_t)(a.lookback[(size_t)(a.n_tiles - 1) * RADIX + d] & LB_VALUE_MASK);  // bucket end
       const int64_t g_prev = t > 0 ? (int64_t)(a.lookback[(size_t)(t - 1) * RADIX + d] & LB_VALUE_MASK) : -1;
       // g == g_prev: tile t put nothing here, the junction coincides with an earlier one
-      if (g < g_end && g > 0 && g != g_prev && ((okey(g - 1) ^ okey(g)) & pmask) == 0) {
-        const int slot = atomicAdd(&q_n, 1);
-        q_g[slot] = g;
-        q_prev[slot] = g_prev;
+      if (g < g_end && g > 0 && g != g_prev) {
+        bool cand;
+        const int64_t g_next = (int64_t)(a.lookback[(size_t)(t + 1) * RADIX + d] & LB_VALUE_MASK);
+        if (a.jtable != nullptr && g_next != g) {
+          // both tiles hold keys of this bucket: compare the fingerprints they left (coalesced reads; the keys
+          // themselves are only fetched for the candidates, below)
+          const uint32_t last_f = (uint32_t)(a.jtable[(size_t)t * RADIX + d] >> 32);
+          const uint32_t first_f = (uint32_t)a.jtable[(size_t)(t + 1) * RADIX + d];
+          cand = last_f == first_f;
+        } else {
+          cand = ((okey(g - 1) ^ okey(g)) & pmask) == 0;
+        }
+        if (cand) {
+          const int slot = atomicAdd(&q_n, 1);
+          q_g[slot] = g;
+          q_prev[slot] = g_prev;
+        }
       }
     }
   }
@@ -287,6 +301,7 @@ __global__ void __launch_bounds__(256) junction_fix_kernel(const __grid_constant
   for (int qi = threadIdx.x; qi < n_q; qi += blockDim.x) {
     const int64_t g = q_g[qi], g_prev = q_prev[qi];
     const O k0 = okey(g - 1);
+    if (((k0 ^ okey(g)) & pmask) != 0) continue;  // equal fingerprints, different segments
     int64_t lo = g - 1, hi = g + 1;
     while (lo > 0 && g - lo <= JF_CAP && ((okey(lo - 1) ^ k0) & pmask) == 0) lo--;
     while (hi < a.n && hi - g <= JF_CAP && ((okey(hi) ^ k0) & pmask) == 0) hi++;

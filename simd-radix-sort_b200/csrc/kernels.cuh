@@ -642,6 +642,9 @@ struct SweepArgs {
   // more than FIX_CAP keys that agree on all swept bits (the full segment finish then has to run)
   uint32_t fix_cut;
   uint32_t *fix_flag;
+  // ... and [n_tiles][RADIX] words {fingerprint of the swept bits of the first key | of the last key << 32} of
+  // this tile's part of every bucket, for junction_fix_kernel
+  uint64_t *jtable;
 };
 
 constexpr int FIX_CAP = 8;   // longest run of keys agreeing on all swept bits that is ordered on the fly
@@ -1118,6 +1121,18 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           }
           if (cr != cl) sdelta[i] = (int8_t)(cr - cl);
         }
+      }
+      // what junction_fix_kernel needs to know about this tile: the swept bits (as a 32-bit fingerprint: equal
+      // bits give equal fingerprints) of the first and the last key of its part of every bucket
+      if (a.jtable != nullptr && tid < RADIX) {
+        const int s0 = (int)s_prefix[tid];
+        const int s1 = min(tid + 1 < RADIX ? (int)s_prefix[tid + 1] : lim, lim);
+        uint64_t w = 0;
+        if (s1 > s0) {
+          const O p0 = (O)key_at(s0) & pmask, p1 = (O)key_at(s1 - 1) & pmask;
+          w = (uint64_t)((uint32_t)((uint64_t)p0 >> 32) ^ (uint32_t)p0) | ((uint64_t)((uint32_t)((uint64_t)p1 >> 32) ^ (uint32_t)p1) << 32);
+        }
+        a.jtable[(size_t)tile * RADIX + tid] = w;
       }
       __syncthreads();
     }
