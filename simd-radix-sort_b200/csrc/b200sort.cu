@@ -203,7 +203,7 @@ cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, int probe, cuda
 struct DevInfo { int sm_count = 0; size_t smem_optin = 0; bool ok = false; };
 static std::mutex g_mu;
 static std::map<int, DevInfo> g_dev;
-struct CacheEntry { void *ptr = nullptr; size_t bytes = 0; };
+struct CacheEntry { void *ptr = nullptr; size_t bytes = 0; uint64_t gen = 0; };  // gen: bumped by every (re)allocation
 static std::map<int, CacheEntry> g_cache;
 
 static int dev_info(int dev, DevInfo *out) {
@@ -239,9 +239,15 @@ static int cached_workspace(int dev, size_t bytes, void **out) {
     }
     c.ptr = p;
     c.bytes = bytes;
+    c.gen++;
   }
   *out = c.ptr;
   return 0;
+}
+
+static uint64_t cached_workspace_gen(int dev) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_cache[dev].gen;
 }
 
 // ------------------------------------------------------------------------------------------------

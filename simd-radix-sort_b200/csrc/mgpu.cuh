@@ -159,6 +159,10 @@ struct DestCountArgs {
   const uint32_t *bounds;      // [world + 1] splitters (bin indices)
   unsigned long long lo;       // bin = range_bin(ordered key, lo, shift, nb)
   uint32_t nb;
+  unsigned long long kbound[7];  // world <= 8: smallest ordered key of rank r+1 (0: every key is at or above it)
+  uint32_t never;                // bit r: no key belongs to rank r+1 or higher (kbound[r] unused)
+  uint32_t hi_only;              // every used kbound is nonzero with a zero low word: compare high words,
+  uint32_t b32m1[7];             // key's high word > b32m1[r]  (0xffffffff: never)
 };
 
 template <int KB, int NLD>
@@ -171,10 +175,34 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
   __syncthreads();
   const int64_t n_tiles = (a.n + KT::TILE - 1) / KT::TILE;
   uint32_t lane_cnt = 0;
+  uint32_t n_ge[7] = {0, 0, 0, 0, 0, 0, 0}, n_all = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     KT kt;
     kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);
-    if (a.world <= 32) {
+    if (a.world <= 8) {
+      // one box: lane-private counters n_ge[r] = number of keys at or above the first key of rank r+1 (the
+      // splitters as 64-bit key values): 7 compares per key, no cross-lane traffic, no table
+      const bool full = kt.valid == (KT::PER_THREAD >= 32 ? 0xffffffffu : ((1u << KT::PER_THREAD) - 1));
+      if (a.hi_only && full) {
+        // splitters with zero low words (full-width keys): one 32-bit compare per splitter
+#pragma unroll
+        for (int i = 0; i < KT::PER_THREAD; i++) {
+          const uint32_t h = KB == 8 ? (uint32_t)((unsigned long long)kt.u[i] >> 32) : (uint32_t)kt.u[i];
+#pragma unroll
+          for (int r = 0; r < 7; r++) n_ge[r] += h > a.b32m1[r] ? 1u : 0u;
+        }
+        n_all += KT::PER_THREAD;
+      } else {
+#pragma unroll
+        for (int i = 0; i < KT::PER_THREAD; i++) {
+          const bool v = (kt.valid >> i) & 1;
+          const unsigned long long u = (unsigned long long)kt.u[i];
+#pragma unroll
+          for (int r = 0; r < 7; r++) n_ge[r] += (v && !((a.never >> r) & 1u) && u >= a.kbound[r]) ? 1u : 0u;
+          n_all += v ? 1u : 0u;
+        }
+      }
+    } else if (a.world <= 32) {
       // few destinations: no table look-up (a random byte load per key is what would bound this kernel).
       // Lane r counts the keys below the upper boundary of rank r: one compare + ballot per rank and row;
       // the counts per destination are the differences.
@@ -196,7 +224,18 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
       }
     }
   }
-  if (a.world <= 32) {
+  if (a.world <= 8) {
+    // counts per destination are differences of the cumulative counters
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t above = r < 7 ? n_ge[r] : 0u;        // keys that belong to ranks > r
+      const uint32_t from = r == 0 ? n_all : n_ge[r - 1];  // keys that belong to ranks >= r
+      uint32_t cnt = from - above;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if ((threadIdx.x & 31) == 0 && r < a.world && cnt) atomicAdd(&sh[r], cnt);
+    }
+  } else if (a.world <= 32) {
     // lane r holds #keys below bound r+1 (cumulative): difference with the lane before gives rank r's count
     const uint32_t prev = __shfl_up_sync(0xffffffffu, lane_cnt, 1);
     const uint32_t mine = lane_cnt - ((threadIdx.x & 31) ? prev : 0u);
@@ -287,6 +326,9 @@ struct b200sort_comm {
   std::vector<cudaIpcMemHandle_t> peer_handle;
   std::vector<void *> peer_base;
   bool p2p_failed = false;                // mapping failed once: stay on the NCCL path
+  cudaIpcMemHandle_t my_handle{};         // handle of this rank's workspace ...
+  void *my_handle_of = nullptr;           // ... taken for this allocation
+  uint64_t my_handle_gen = 0;
   bool last_p2p = false;
 };
 
@@ -495,16 +537,34 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   MgpuBlob mine{};
   const bool want_p2p = opt_mgpu_p2p.load() != 0 && !c->p2p_failed;
   if (want_p2p) {
-    cudaError_t e = cudaIpcGetMemHandle(&mine.handle, ws);
-    if (e != cudaSuccess) { cudaGetLastError(); c->p2p_failed = true; }
+    const uint64_t gen = cached_workspace_gen(c->dev);
+    if (c->my_handle_of != ws || c->my_handle_gen != gen) {  // (a slow driver call: once per workspace allocation)
+      cudaError_t e = cudaIpcGetMemHandle(&c->my_handle, ws);
+      if (e != cudaSuccess) { cudaGetLastError(); c->p2p_failed = true; }
+      else { c->my_handle_of = ws; c->my_handle_gen = gen; }
+    }
+    mine.handle = c->my_handle;
   }
   mine.ws_bytes = L.total;
   mine.capacity = capacity;
   mine.p2p = (want_p2p && !c->p2p_failed) ? 1 : 0;
   MgpuBlob *my_slot = c->d_blob + c->rank;
   CUDA_TRY(cudaMemcpyAsync(my_slot, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));  // counts zeroed with it
+  trace.mark("host_prep");
   if (num_local > 0) {
-    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts, world, c->d_bounds, lo, nb};
+    DestCountArgs da{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, shift, c->d_lut, my_slot->counts, world, c->d_bounds, lo, nb, {}, 0u, 1u, {}};
+    for (int r = 0; r < 7; r++) {
+      // range_bin(u) >= bounds[r+1]  <=>  u >= lo + (bounds[r+1] << shift), with the two clamps of range_bin
+      const uint32_t ubr = r + 1 < world ? bounds[r + 1] : nb;
+      da.kbound[r] = ubr >= nb ? ~0ull : (ubr == 0 ? 0ull : lo + ((unsigned long long)ubr << shift));
+      if (ubr >= nb) da.never |= 1u << r;
+      // fast form: high word of the key (the whole key for <= 4-byte keys) against the splitter's high word
+      const unsigned long long kbv = da.kbound[r];
+      const uint32_t hw = kb == 8 ? (uint32_t)(kbv >> 32) : (uint32_t)kbv;
+      if (ubr >= nb) da.b32m1[r] = 0xffffffffu;
+      else if (kbv == 0 || hw == 0 || (kb == 8 && (uint32_t)kbv != 0)) da.hi_only = 0;
+      else da.b32m1[r] = hw - 1u;
+    }
     CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
   }
   trace.mark("count");
