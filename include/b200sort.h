@@ -17,7 +17,8 @@
  *  - the sort is in place from the caller's point of view (reference: radix_sort.hpp:297-337): the
  *    result overwrites keys/payloads/records.  Scratch (one shadow copy of every stream + per-tile
  *    status words) comes from `workspace` or, when that is NULL, from a per-device cache owned by
- *    the library.
+ *    the library.  Sorts that use that cache (and all host-memory calls, which stage through a cached
+ *    buffer) are serialised per device by the library; give concurrent sorts their own workspaces.
  *  - return value: 0 on success, a negative B200SORT_E* code otherwise; b200sort_last_error() gives
  *    a thread-local human-readable message.  There is NO CPU fallback: without a usable CUDA device
  *    every sort call fails with B200SORT_ECUDA.

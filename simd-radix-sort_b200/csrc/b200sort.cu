@@ -206,6 +206,33 @@ static std::map<int, DevInfo> g_dev;
 struct CacheEntry { void *ptr = nullptr; size_t bytes = 0; uint64_t gen = 0; };  // gen: bumped by every (re)allocation
 static std::map<int, CacheEntry> g_cache;
 
+// The library-owned caches (workspace, host staging) are one allocation per device.  Sorts that use them are
+// serialised: a per-device (recursive) mutex covers the launching of a sort, and the stream of the next sort
+// waits for an event recorded at the end of the previous one, so that two host threads, or two streams, never
+// have kernels in flight on the same scratch memory.  Callers who want concurrent sorts pass their own workspace.
+struct CacheGuardState { std::recursive_mutex mu; cudaEvent_t last_use = nullptr; };
+static CacheGuardState &cache_guard_state(int dev) {
+  static std::map<int, CacheGuardState> g_guard;
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_guard[dev];  // (std::map nodes are stable)
+}
+struct CacheGuard {
+  CacheGuardState *st = nullptr;
+  cudaStream_t stream = nullptr;
+  void acquire(int dev, cudaStream_t s) {
+    st = &cache_guard_state(dev);
+    stream = s;
+    st->mu.lock();
+    if (st->last_use == nullptr) cudaEventCreateWithFlags(&st->last_use, cudaEventDisableTiming);
+    else cudaStreamWaitEvent(stream, st->last_use, 0);
+  }
+  ~CacheGuard() {
+    if (!st) return;
+    cudaEventRecord(st->last_use, stream);
+    st->mu.unlock();
+  }
+};
+
 static int dev_info(int dev, DevInfo *out) {
   std::lock_guard<std::mutex> lk(g_mu);
   DevInfo &d = g_dev[dev];
@@ -352,7 +379,9 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   Layout L;
   make_layout(streams, std::max(n, layout_n), std::min(tile, HYB_MIN_TILE), &L, xo.layout_landing);
   void *const caller_workspace = workspace;
+  CacheGuard cache_guard;  // released (and its event recorded) when this sort has been launched
   if (workspace == nullptr) {
+    cache_guard.acquire(dev, stream);
     if (int rc = cached_workspace(dev, L.total, &workspace)) return rc;
   } else if (workspace_bytes < L.total) {
     return fail(B200SORT_ENOMEM, "workspace of %zu bytes given, %zu needed", workspace_bytes, L.total);
@@ -713,6 +742,8 @@ static int sort_host_pipelined(int key_type, bool ascending, int64_t n, const st
     off_in[s] = total;  total = align_up(total + (size_t)n * streams[s + 1].elem_bytes, 256);
     off_out[s] = total; total = align_up(total + (size_t)n * streams[s + 1].elem_bytes, 256);
   }
+  CacheGuard cache_guard;  // the staging buffer is shared per device as well; this call is synchronous anyway
+  cache_guard.acquire(dev, caller);
   void *dbuf_v = nullptr;
   if (int rc = cached_stage(dev, total, &dbuf_v)) return rc;
   unsigned char *dbuf = (unsigned char *)dbuf_v;

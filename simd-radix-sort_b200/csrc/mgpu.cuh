@@ -489,6 +489,8 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
                        opt_mgpu_landing.load() != 0 && opt_mgpu_p2p.load() != 0;
   Layout L;
   make_layout(streams, n_ws, std::min(tile, HYB_MIN_TILE), &L, landing);
+  CacheGuard cache_guard;  // (recursive: the local sort below takes it again)
+  cache_guard.acquire(c->dev, stream);
   void *ws_v = nullptr;
   if (int rc = cached_workspace(c->dev, L.total, &ws_v)) return rc;
   unsigned char *ws = (unsigned char *)ws_v;
