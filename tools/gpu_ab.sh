@@ -1,4 +1,5 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --e2e-steps 2 --cpu-sample 0 2>&1 | tail -1 | cut -c1-700
+SB=./simd-radix-sort_b200/sortbench
+timeout 300 $SB --n 4400000000 --key u8 --iters 1 --prof
+timeout 300 $SB --n 4300000000 --key u16 --pay 1 --iters 1 --prof --desc
+timeout 300 $SB --n 2200000000 --key i64 --pay 4 --iters 1 --prof
