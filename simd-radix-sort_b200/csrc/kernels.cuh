@@ -1215,7 +1215,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   // CTAs per tile stagger naturally.  profiles/README.md)
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
-  for (int i = threadIdx.x; i < NWARPS * RADIX; i += THREADS) warp_cnt[i] = 0;
+  for (int i = threadIdx.x; i < NWARPS * RADIX / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
   __syncthreads();
   const int64_t tile = s_tile;
