@@ -102,3 +102,26 @@ def test_splitters_balance_and_cover():
                                      bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) == 0
     loads = [int(hist[bounds[r]:bounds[r + 1]].sum()) for r in range(4)]
     assert sum(loads) == 1000 and max(loads) == 1000
+
+
+def test_splitters_prefer_aligned_boundaries():
+    """near-uniform histograms and a power-of-two world: every boundary lands on a multiple of 2^bits / world,
+    so each shard's keys share their leading log2(world) bits (what the local sort's left-shifted plan needs)"""
+    L = S.lib()
+    rng = np.random.default_rng(5)
+    bits = 16
+    for world in (2, 4, 8):
+        hist = rng.poisson(250.0, size=1 << bits).astype(np.uint64)  # a 2^24-key sample of uniform keys
+        bounds = np.zeros(world + 1, np.uint32)
+        assert L.b200sort_mgpu_splitters(hist.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), bits, world,
+                                         bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) == 0
+        step = (1 << bits) // world
+        assert bounds.tolist() == [r * step for r in range(world + 1)], bounds
+    # a skewed histogram must not be forced onto aligned boundaries at the price of balance
+    hist = np.ones(1 << bits, np.uint64)
+    hist[: 1 << 12] = 1000
+    bounds = np.zeros(5, np.uint32)
+    assert L.b200sort_mgpu_splitters(hist.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), bits, 4,
+                                     bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) == 0
+    loads = np.array([hist[bounds[r]:bounds[r + 1]].sum() for r in range(4)], dtype=np.float64)
+    assert np.all(np.abs(loads - hist.sum() / 4) <= hist.sum() / 4 / 32 + 1001), loads
