@@ -45,6 +45,7 @@ static std::atomic<int64_t> opt_fix_in_pass{1};  // order tile-local segments in
 static std::atomic<int64_t> opt_hist_match{0};
 static std::atomic<int64_t> opt_margin_bits{2};
 static std::atomic<int64_t> opt_probe_guess{1};
+static std::atomic<int64_t> opt_probe_sample{16};  // large sorts: every this-many-th tile feeds the sampled histograms
 static std::atomic<int64_t> opt_allow_lshift{1};
 static std::atomic<int64_t> opt_junction_table{1};  // junction kernel compares fingerprints left by the last pass
 static std::atomic<int64_t> opt_host_pipeline{1};  // host SoA arrays: sort keys + index while the payloads upload
@@ -439,9 +440,9 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
     {
       const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
-      // entropies from one key per thread of every 8th tile once there are plenty of tiles
+      // entropies from one key per thread of every 16th tile (option probe_sample) once there are plenty of tiles
       const bool sparse = (n / tile_keys) >= 8192;
-      ha.sample = sparse ? 8 : 1;
+      ha.sample = sparse ? (uint32_t)std::max<int64_t>(1, opt_probe_sample.load()) : 1;
       ha.sample_one = sparse ? 1 : 0;
     }
     // Large sorts leave the exact key range to a sweep of its own that only runs when the sampled range says
@@ -997,6 +998,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "profile")) return &opt_profile;
   if (!strcmp(name, "margin_bits")) return &opt_margin_bits;
   if (!strcmp(name, "probe_guess")) return &opt_probe_guess;
+  if (!strcmp(name, "probe_sample")) return &opt_probe_sample;
   if (!strcmp(name, "allow_lshift")) return &opt_allow_lshift;
   if (!strcmp(name, "mgpu_p2p")) return &opt_mgpu_p2p;
   if (!strcmp(name, "mgpu_landing")) return &opt_mgpu_landing;
