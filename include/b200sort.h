@@ -143,6 +143,9 @@ int b200sort_mgpu_comm_destroy(b200sort_comm *comm);
 /* 1 if the last b200sort_mgpu_sort_soa on this communicator scattered its records straight into the peers'
  * memory (cudaIpc-mapped workspaces over NVLink), 0 if it exchanged them with ncclSend/ncclRecv. */
 int b200sort_mgpu_used_p2p(const b200sort_comm *comm);
+/* Note: while a communicator is alive its peers may have this process's cached workspace mapped.  The library
+ * makes them let go before b200sort_mgpu_sort_soa re-allocates it; do not call b200sort_release_cache(), or a
+ * larger single-GPU sort with workspace == NULL, between multi-GPU sorts without destroying the communicator. */
 
 /* Host-side splitter selection used by the multi-GPU sort (exported so that it can be tested without
  * a GPU): given the globally reduced histogram of the top `bits` bits of the order-mapped keys

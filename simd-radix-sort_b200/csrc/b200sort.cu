@@ -273,6 +273,11 @@ static int cached_workspace(int dev, size_t bytes, void **out) {
   return 0;
 }
 
+static size_t cached_workspace_bytes(int dev) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_cache[dev].bytes;
+}
+
 static uint64_t cached_workspace_gen(int dev) {
   std::lock_guard<std::mutex> lk(g_mu);
   return g_cache[dev].gen;

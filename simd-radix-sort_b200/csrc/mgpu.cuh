@@ -396,7 +396,7 @@ int b200sort_mgpu_comm_create(b200sort_comm **out, int world_size, int rank, con
   CUDA_TRY(cudaGetDevice(&c->dev));
   NCCL_TRY(api.CommInitRank(&c->comm, world_size, id, rank));
   CUDA_TRY(cudaMalloc(&c->d_hist, sizeof(unsigned long long) << MGPU_MAX_BITS));
-  CUDA_TRY(cudaMalloc(&c->d_counts, sizeof(unsigned long long) * (size_t)world_size * (world_size + 1)));
+  CUDA_TRY(cudaMalloc(&c->d_counts, sizeof(unsigned long long) * ((size_t)world_size * (world_size + 1) + 8)));
   CUDA_TRY(cudaMalloc(&c->d_lut, (size_t)1 << MGPU_MAX_BITS));
   CUDA_TRY(cudaMalloc(&c->d_bin_base, sizeof(uint64_t) * RADIX));
   CUDA_TRY(cudaMalloc(&c->d_plan, sizeof(Plan)));
@@ -491,22 +491,35 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   make_layout(streams, n_ws, std::min(tile, HYB_MIN_TILE), &L, landing);
   CacheGuard cache_guard;  // (recursive: the local sort below takes it again)
   cache_guard.acquire(c->dev, stream);
-  void *ws_v = nullptr;
-  if (int rc = cached_workspace(c->dev, L.total, &ws_v)) return rc;
-  unsigned char *ws = (unsigned char *)ws_v;
-  for (size_t s = 0; s < streams.size(); s++) ss.streams[s].buf[1] = ws + L.shadow_off[s];
+  // A rank whose cached workspace is too small is going to free and re-allocate it.  Its peers may still have
+  // the old allocation mapped (cudaIpcOpenMemHandle): they have to let go of it first.  The flag travels with
+  // the first all-reduce below.
+  const bool will_realloc = cached_workspace_bytes(c->dev) < L.total;
 
   // 1: key range of a sample of all ranks' keys (min / max all-reduced), then the histogram of that range in
   //    2^bits bins on the same sample, all-reduced
   const int64_t sample = std::max<int64_t>(1, num_local >> 24);  // about 2^24 sampled keys at most
-  unsigned long long range_h[2] = {~0ull, ~0ull};
+  unsigned long long range_h[3] = {~0ull, ~0ull, will_realloc ? 0ull : 1ull};
   CUDA_TRY(cudaMemcpyAsync(c->d_counts, range_h, sizeof range_h, cudaMemcpyHostToDevice, stream));
   TopHistArgs ha{(const unsigned char *)keys, (uint32_t)kb, num_local, ko, 0, c->d_hist, sample, 0ull, nb, c->d_counts};
   if (num_local > 0) CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream, /*range_only=*/true));
-  NCCL_TRY(api.AllReduce(c->d_counts, c->d_counts, 2, ncclUint64, ncclMin, c->comm, stream));
+  NCCL_TRY(api.AllReduce(c->d_counts, c->d_counts, 3, ncclUint64, ncclMin, c->comm, stream));
   CUDA_TRY(cudaMemcpyAsync(range_h, c->d_counts, sizeof range_h, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned long long) * nb, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
+  if (range_h[2] == 0) {
+    // somebody re-allocates: every rank drops all its mappings, and nobody frees anything before all have
+    for (int r = 0; r < world; r++) {
+      if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+      c->peer_base[r] = nullptr;
+    }
+    NCCL_TRY(api.AllReduce(c->d_counts + 4, c->d_counts + 4, 1, ncclUint64, ncclSum, c->comm, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  void *ws_v = nullptr;
+  if (int rc = cached_workspace(c->dev, L.total, &ws_v)) return rc;
+  unsigned char *ws = (unsigned char *)ws_v;
+  for (size_t s = 0; s < streams.size(); s++) ss.streams[s].buf[1] = ws + L.shadow_off[s];
   unsigned long long lo = range_h[0], hi = ~range_h[1];
   if (lo > hi) lo = hi = 0;  // no keys anywhere
   int shift = 0;
