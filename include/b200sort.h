@@ -153,6 +153,10 @@ int b200sort_mgpu_used_p2p(const b200sort_comm *comm);
  * rank r owns bins [b[r], b[r+1]) and the loads are even to within bin granularity plus 1/64 of a share,
  * which a boundary may give up to land on an aligned bin index (shards then share leading key bits). */
 int b200sort_mgpu_splitters(const uint64_t *global_hist, int bits, int world_size, uint32_t *out_bounds);
+/* The binning of that histogram: from the smallest / largest order-mapped key of the ranks' samples to
+ * bin(u) = clamp((u - lo) >> shift, 0, 2^bits - 1).  Keys of a narrow range get bins as fine as single values;
+ * full-width keys keep bin = their top `bits` bits.  Exported for the same reason. */
+int b200sort_mgpu_range_bins(uint64_t lo_key, uint64_t hi_key, int key_bytes, int bits, uint64_t *out_lo, int *out_shift);
 
 /* Host-side exchange plan (also exported for GPU-less tests): number of local records destined to each
  * rank, given this rank's own top-bits histogram and the splitters above. */

@@ -262,6 +262,22 @@ static cudaError_t launch_dest_count(int kb, const DestCountArgs &a, int sm_coun
   return cudaGetLastError();
 }
 
+// From the smallest / largest sampled ordered key to the binning of the splitter histogram:
+// bin(u) = clamp((u - lo) >> shift, 0, 2^bits - 1)  (range_bin(), kernels.cuh).
+static void choose_range_bins(unsigned long long lo_key, unsigned long long hi_key, int key_bytes, int bits,
+                              unsigned long long *out_lo, int *out_shift) {
+  unsigned long long lo = lo_key, hi = hi_key;
+  if (lo > hi) lo = hi = 0;  // no keys anywhere
+  const unsigned long long span = hi - lo;
+  const int span_bits = span ? 64 - __builtin_clzll(span) : 0;
+  int shift = std::max(0, span_bits - bits);
+  // full-width keys: keep the bins aligned with the key's own leading bits (the local sorts then see shards
+  // with constant leading bits and can shift them out)
+  if (span_bits > 8 * key_bytes - 2) { lo = 0; shift = 8 * key_bytes - bits; }
+  *out_lo = lo;
+  *out_shift = shift;
+}
+
 // Splitters on bin boundaries.  Rank r ideally ends where the running count reaches r/world of the total; any
 // boundary whose prefix is within 1/64 of a rank's share of that target is acceptable (capacities leave
 // 1/8), and among those the one with the most trailing zero bits wins: the keys of a shard then agree on as
@@ -424,6 +440,16 @@ int b200sort_mgpu_comm_destroy(b200sort_comm *c) {
 
 int b200sort_mgpu_used_p2p(const b200sort_comm *c) { return c && c->last_p2p ? 1 : 0; }
 
+int b200sort_mgpu_range_bins(uint64_t lo_key, uint64_t hi_key, int key_bytes, int bits, uint64_t *out_lo, int *out_shift) {
+  using namespace b200sort;
+  if (!out_lo || !out_shift || bits < 1 || bits > MGPU_MAX_BITS || (key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8))
+    return fail(B200SORT_EINVAL, "bad range arguments");
+  unsigned long long lo = 0;
+  choose_range_bins(lo_key, hi_key, key_bytes, std::min(bits, 8 * key_bytes), &lo, out_shift);
+  *out_lo = lo;
+  return 0;
+}
+
 int b200sort_mgpu_splitters(const uint64_t *global_hist, int bits, int world_size, uint32_t *out_bounds) {
   using namespace b200sort;
   if (!global_hist || !out_bounds || bits < 1 || bits > MGPU_MAX_BITS || world_size < 1 || world_size > RADIX)
@@ -520,17 +546,9 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   if (int rc = cached_workspace(c->dev, L.total, &ws_v)) return rc;
   unsigned char *ws = (unsigned char *)ws_v;
   for (size_t s = 0; s < streams.size(); s++) ss.streams[s].buf[1] = ws + L.shadow_off[s];
-  unsigned long long lo = range_h[0], hi = ~range_h[1];
-  if (lo > hi) lo = hi = 0;  // no keys anywhere
+  unsigned long long lo = 0;
   int shift = 0;
-  {
-    const unsigned long long span = hi - lo;
-    const int span_bits = span ? 64 - __builtin_clzll(span) : 0;
-    shift = std::max(0, span_bits - bits);
-    // full-width keys: keep the bins aligned with the key's own leading bits (the local sorts then see shards
-    // with constant leading bits and can shift them out)
-    if (span_bits > 8 * kb - 2) { lo = 0; shift = 8 * kb - bits; }
-  }
+  choose_range_bins(range_h[0], ~range_h[1], kb, bits, &lo, &shift);
   ha.lo = lo; ha.shift = shift;
   if (num_local > 0) CUDA_TRY(launch_top_hist(kb, ha, di.sm_count, stream));
   std::vector<uint64_t> global_hist(nb);

@@ -125,3 +125,37 @@ def test_splitters_prefer_aligned_boundaries():
                                      bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) == 0
     loads = np.array([hist[bounds[r]:bounds[r + 1]].sum() for r in range(4)], dtype=np.float64)
     assert np.all(np.abs(loads - hist.sum() / 4) <= hist.sum() / 4 / 32 + 1001), loads
+
+
+def test_range_bins_make_narrow_key_ranges_splittable():
+    """the splitter histogram covers the sampled key range, not the key space: N(0, 1000) int64 keys (two
+    distinct top-16-bit values!) still split evenly over 8 ranks; full-width keys keep bin = top 16 bits"""
+    L = S.lib()
+    u64p, u32p = ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)
+    L.b200sort_mgpu_range_bins.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, u64p, ctypes.POINTER(ctypes.c_int)]
+    import oracle_lib as O
+    rng = np.random.default_rng(11)
+    bits, nb = 16, 1 << 16
+    for name, keys in (("gauss_i64", np.round(rng.normal(0, 1000, 400_000)).astype(np.int64)),
+                       ("uniform_u64", rng.integers(0, 2**64, 400_000, dtype=np.uint64)),
+                       ("small_u32", rng.integers(0, 5000, 400_000, dtype=np.uint32)),
+                       ("f64_unit", rng.uniform(-1, 1, 400_000))):
+        u = O.order_key(keys, True).astype(np.uint64)
+        sample = u[::7]
+        lo, shift = ctypes.c_uint64(0), ctypes.c_int(0)
+        assert L.b200sort_mgpu_range_bins(int(sample.min()), int(sample.max()), keys.dtype.itemsize, bits, ctypes.byref(lo), ctypes.byref(shift)) == 0
+        lo, shift = np.uint64(lo.value), np.uint64(shift.value)
+        # range_bin() of csrc/kernels.cuh, restated
+        b = np.where(u <= lo, np.uint64(0), np.minimum((u - lo) >> shift, np.uint64(nb - 1))).astype(np.int64)
+        assert np.all(np.diff(b[np.argsort(u, kind="stable")]) >= 0), name  # monotonic in the key
+        if name == "uniform_u64":
+            assert lo == 0 and shift == 48
+        hist = np.bincount(b, minlength=nb).astype(np.uint64)
+        world = 8
+        bounds = np.zeros(world + 1, np.uint32)
+        assert L.b200sort_mgpu_splitters(hist.ctypes.data_as(u64p), bits, world, bounds.ctypes.data_as(u32p)) == 0
+        loads = np.array([hist[bounds[r]:bounds[r + 1]].sum() for r in range(world)], dtype=np.float64)
+        ideal = len(keys) / world
+        assert loads.max() <= ideal * (1 + 1 / 32) + hist.max() + 1, (name, loads)
+        if name != "small_u32":
+            assert loads.max() <= 1.2 * ideal, (name, loads)  # what the default capacity (1.125x + slack) tolerates
