@@ -842,7 +842,12 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   auto digit_of = [&](int r) -> uint32_t { return (dpack[r >> 2] >> (8 * (r & 3))) & (RADIX - 1); };
 
   // ---- rank inside the warp (stable) -----------------------------------------------------------------
-  uint32_t rank[IPT];
+  // ranks (< TILE <= 65536) are kept two to a register: the kernel is at its register limit for 3 CTAs/SM
+  uint32_t rankp[IPT / 2];
+  auto rank_get = [&](int r) -> uint32_t { return (r & 1) ? (rankp[r >> 1] >> 16) : (rankp[r >> 1] & 0xffffu); };
+  auto rank_set = [&](int r, uint32_t v) { rankp[r >> 1] = (r & 1) ? ((rankp[r >> 1] & 0xffffu) | (v << 16)) : ((rankp[r >> 1] & 0xffff0000u) | v); };
+#pragma unroll
+  for (int q = 0; q < IPT / 2; q++) rankp[q] = 0;
   uint32_t *wc = warp_cnt + warp * RADIX;
   // the pass executed after this one gets its exact digit histogram from here (keys are in registers)
   const uint32_t next_p1 = LUT ? 0u : (a.plan_in_args ? a.arg_next_p1 : a.plan->next_exec_p1[a.pass]);
@@ -871,7 +876,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     const uint32_t cnt = wc[d];
     __syncwarp();
     const uint32_t lower = __popc(peers & lanemask_lt());
-    rank[r] = cnt + lower;
+    rank_set(r, cnt + lower);
     if (lower == 0) wc[d] = cnt + __popc(peers);
     __syncwarp();
   }
@@ -944,9 +949,10 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
     const uint32_t d = digit_of(r);
-    rank[r] += s_prefix[d] + wc[d];
-    sdigit[rank[r]] = (uint8_t)d;
-    srank[idx0 + r * 32] = (uint16_t)rank[r];  // payload streams pick their slot up from here
+    const uint32_t rk = rank_get(r) + s_prefix[d] + wc[d];
+    rank_set(r, rk);
+    sdigit[rk] = (uint8_t)d;
+    srank[idx0 + r * 32] = (uint16_t)rk;  // payload streams pick their slot up from here
   }
 
   // ---- the column pipeline.  Column 0 is the key array itself (SoA: staged from registers) or the first
@@ -977,7 +983,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
     for (int r = 0; r < IPT; r++)
       if (FULL || idx0 + r * 32 < n_valid) {
-        kst[rank[r]] = raw[r];
+        kst[rank_get(r)] = raw[r];
       }
   } else {
     issue_next(bufs[0]);
