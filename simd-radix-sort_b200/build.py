@@ -16,7 +16,10 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb200sort.so"
-SOURCES = [CSRC / "b200sort.cu"] + [CSRC / f"sweep_kb{k}.cu" for k in (1, 2, 4, 8)]
+# (source, object stem, extra defines): sweep_inst.cu is compiled once per (key bytes, tile geometry)
+UNITS = [(CSRC / "b200sort.cu", "b200sort", [])] + [
+    (CSRC / "sweep_inst.cu", f"sweep_kb{k}_c{c}", [f"-DSWEEP_KB={k}", f"-DSWEEP_CFG={c}"]) for k in (8, 4, 2, 1) for c in (0, 1)]
+SOURCES = [CSRC / "b200sort.cu", CSRC / "sweep_inst.cu"]
 HEADERS = [CSRC / "kernels.cuh", CSRC / "hybrid.cuh", CSRC / "mgpu.cuh", CSRC / "sweep_select.cuh", PKG.parent / "include" / "b200sort.h"]
 
 NVCC_FLAGS = [
@@ -50,20 +53,21 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
     newest_header = max(h.stat().st_mtime for h in HEADERS if h.exists())
 
-    def compile_one(src: Path) -> Path:
-        obj = objdir / (src.stem + ".o")
+    def compile_one(unit) -> Path:
+        src, stem, defines = unit
+        obj = objdir / (stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_header):
             return obj
-        cmd = [nvcc_path(), *compile_flags, "-c", "-o", str(obj), str(src)]
+        cmd = [nvcc_path(), *compile_flags, *defines, "-c", "-o", str(obj), str(src)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}\n{r.stderr}")
+            raise RuntimeError(f"nvcc failed on {src.name} {defines}:\n{r.stdout}\n{r.stderr}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, [s for s in SOURCES if s.exists()]))
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
     cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
            *[str(o) for o in objs], "-ldl"]
     if verbose:

@@ -37,7 +37,6 @@ static std::atomic<uint64_t> g_launches{0};
 
 static std::atomic<int64_t> opt_algo{0};       // 0 auto, 1 LSD, 2 hybrid
 static std::atomic<int64_t> opt_tile_cfg{-1};  // -1 auto
-static std::atomic<int64_t> opt_use_match{0};
 static std::atomic<int64_t> opt_allow_skip{1};
 static std::atomic<int64_t> opt_allow_reduce{1};
 static std::atomic<int64_t> opt_spin_ns{0};
@@ -55,23 +54,24 @@ static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at l
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
 enum ProfKind { PK_HIST = 0, PK_SCAN = 1, PK_SWEEP = 2, PK_COPYBACK = 3, PK_SEGFIX = 4, PK_OTHER = 5 };
-struct ProfEntry { int kind; cudaEvent_t e0, e1; };
+struct ProfEntry { int kind; cudaEvent_t e0, e1; int dev; };
 static std::atomic<int64_t> opt_profile{0};
 static thread_local std::vector<ProfEntry> g_prof;
-static thread_local std::vector<cudaEvent_t> g_prof_pool;
+static thread_local std::map<int, std::vector<cudaEvent_t>> g_prof_pool;  // per device: events belong to one
 
 static void prof_reset() {
-  for (auto &p : g_prof) { g_prof_pool.push_back(p.e0); g_prof_pool.push_back(p.e1); }
+  for (auto &p : g_prof) { g_prof_pool[p.dev].push_back(p.e0); g_prof_pool[p.dev].push_back(p.e1); }
   g_prof.clear();
 }
-static cudaEvent_t prof_event() {
-  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+static cudaEvent_t prof_event(int dev) {
+  auto &pool = g_prof_pool[dev];
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct ProfScope {
   bool on; ProfEntry pe; cudaStream_t st;
   ProfScope(int kind, cudaStream_t s) : on(opt_profile.load() != 0), st(s) {
-    if (on) { pe.kind = kind; pe.e0 = prof_event(); pe.e1 = prof_event(); cudaEventRecord(pe.e0, st); }
+    if (on) { pe.dev = 0; cudaGetDevice(&pe.dev); pe.kind = kind; pe.e0 = prof_event(pe.dev); pe.e1 = prof_event(pe.dev); cudaEventRecord(pe.e0, st); }
   }
   ~ProfScope() { if (on) { cudaEventRecord(pe.e1, st); g_prof.push_back(pe); } }
 };
@@ -122,16 +122,35 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
-static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false, bool lut = false) {
+static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false, bool lut = false, int rank = RANK_MATCH) {
   const size_t tile = (size_t)c.threads * c.ipt;
-  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 +
+  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 * (rank == RANK_MATCH ? 3 : 1) + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 +
          (fix ? tile : 0) +       // FIX: per-slot displacement
          (lut ? RADIX * 8 : 0);   // LUT: peer byte offsets
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
+static std::atomic<int64_t> opt_rank_mode{1};     // stable ranking: 0 ballots, 1 atomicOr match
+static std::atomic<int64_t> opt_first_atomic{1};  // first executed pass of a large sort: unstable atomicAdd ranking
+static std::atomic<int64_t> opt_idx32{1};         // 32-bit destination offsets when n < 2^32
 
-static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int sm_count, cudaStream_t st) {
+inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
+  switch (kb * 2 + cfg) {
+    case 2: return sweep_fn_inst<1, 0>(s);
+    case 3: return sweep_fn_inst<1, 1>(s);
+    case 4: return sweep_fn_inst<2, 0>(s);
+    case 5: return sweep_fn_inst<2, 1>(s);
+    case 8: return sweep_fn_inst<4, 0>(s);
+    case 9: return sweep_fn_inst<4, 1>(s);
+    case 16: return sweep_fn_inst<8, 0>(s);
+    default: return sweep_fn_inst<8, 1>(s);
+  }
+}
+
+// first_pass_unordered: the caller knows that this launch is the first executed pass of the sort and that its
+// digit's histogram is not skewed -- the unstable ranking may be used
+static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int sm_count, cudaStream_t st,
+                                bool first_pass_unordered = false) {
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   int n_cols = 0;
   const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == (uint32_t)kb;
@@ -141,22 +160,19 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   }
   n_cols += soa ? 1 : 0;
   const TileCfg tc = kTileCfgs[cfg];
+  const bool lut = a.lut != nullptr;
+  const bool fix = !lut && a.fix_cut != 0;  // (the caller only sets fix_cut where the FIX instantiation exists)
+  int rank = opt_rank_mode.load() != 0 ? RANK_MATCH : RANK_BALLOT;
+  if (first_pass_unordered && !lut && !fix && opt_first_atomic.load() != 0) rank = RANK_ATOMIC;
   // double-buffer the columns when there is more than one and minb CTAs still fit on an SM
   int nstage = (int)opt_nstage.load();
   if (nstage != 1 && nstage != 2)
-    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * tc.minb <= smem_optin + 1024) ? 2 : 1;
-  if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2) > smem_optin) nstage = 1;
-  const bool lut = a.lut != nullptr;
-  const bool fix = !lut && a.fix_cut != 0;  // (the caller only sets fix_cut where the FIX instantiation exists)
+    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2, false, false, rank) + 1024) * tc.minb <= smem_optin + 1024) ? 2 : 1;
+  if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2, false, false, rank) > smem_optin) nstage = 1;
   if (lut || fix) nstage = 1;
-  SweepFn k;
-  switch (kb) {
-    case 1: k = sweep_fn_kb1(cfg, nstage, any, lut, fix); break;
-    case 2: k = sweep_fn_kb2(cfg, nstage, any, lut, fix); break;
-    case 4: k = sweep_fn_kb4(cfg, nstage, any, lut, fix); break;
-    default: k = sweep_fn_kb8(cfg, nstage, any, lut, fix); break;
-  }
-  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut);
+  SweepSel sel{nstage, any || lut, lut, fix, rank, !lut && opt_idx32.load() != 0 && a.n < ((int64_t)1 << 32)};
+  SweepFn k = sweep_fn(kb, cfg, sel);
+  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut, rank);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
@@ -299,9 +315,9 @@ struct Layout {
 
 static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin) {
   int cfg = (int)opt_tile_cfg.load();
-  if (cfg < 0 || cfg >= kNumTileCfgs) cfg = 1;
-  // fall back to a smaller tile if the staging buffer would not fit
-  while (sweep_smem_bytes(kTileCfgs[cfg], stage_bytes) > smem_optin && cfg != 1) cfg = 1;
+  if (cfg < 0 || cfg >= kNumTileCfgs) cfg = kDefaultTileCfg;
+  // fall back to the smaller tile if the staging buffer would not fit
+  if (sweep_smem_bytes(kTileCfgs[cfg], stage_bytes) > smem_optin) cfg = 1;
   return cfg;
 }
 
@@ -349,7 +365,17 @@ struct DevSortOpts {
   bool landing_input = false;   // the input lies in the landing arrays: the first executed pass reads it from
                                 // there (landing -> shadow -> caller -> ...), so that an even number of passes
                                 // ends in the caller's arrays without a copy
+  int force_algo = 0;           // 1 / 2: use this algorithm whatever option "algo" says (the hybrid path's fall-back)
 };
+
+// one event per device for the plan read-back of large sorts (an event belongs to the device it was created on)
+static cudaEvent_t plan_event_of(int dev) {
+  static std::map<int, cudaEvent_t> g_plan_events;
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaEvent_t &e = g_plan_events[dev];
+  if (e == nullptr && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) e = nullptr;
+  return e;
+}
 static int sort_device(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams,
                        cudaStream_t stream, void *workspace, size_t workspace_bytes, const DevSortOpts &xo = DevSortOpts()) {
   const int start_sel = xo.start_sel;
@@ -407,7 +433,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
 
   const KeyOrder ko = make_key_order(key_type, ascending);
 
-  int algo = (int)opt_algo.load();
+  int algo = xo.force_algo != 0 ? xo.force_algo : (int)opt_algo.load();
   if (algo == 0) algo = (kb == 8 && n >= HYB_MIN_N) ? 2 : 1;
   if (algo == 2 && kb != 8) algo = 1;
 
@@ -498,12 +524,13 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     // needed returns at once.
     Plan hplan{};
     bool have_plan = false;
-    static thread_local cudaEvent_t plan_event = nullptr;
+    cudaEvent_t plan_event = nullptr;
     HistArgs hb = ha;
     hb.ghist = ghist_exact; hb.plan = plan; hb.probe = nullptr;
     uint32_t hist_sweeps = 1;
     if (big) {
-      if (plan_event == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&plan_event, cudaEventDisableTiming));
+      plan_event = plan_event_of(dev);
+      if (plan_event == nullptr) return fail(B200SORT_ECUDA, "cudaEventCreate failed on device %d", dev);
       CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaEventRecord(plan_event, stream));
       CUDA_TRY(cudaEventSynchronize(plan_event));
@@ -533,7 +560,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     // holds and repairs the tile-straddling ones with junction_fix_kernel; the full segment finish then only
     // runs if one of them reports a run that is too long.
     const bool soa = streams[0].elem_bytes == (uint32_t)kb;
-    const bool use_fix = have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == 1 && opt_fix_in_pass.load() != 0;
+    const bool use_fix = have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == kDefaultTileCfg && opt_fix_in_pass.load() != 0;
     int last_pass = -1;
     bool first_exec = true;
     if (landing && hplan.n_exec == 0) {  // nothing will move the records: deliver them
@@ -543,6 +570,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       if (have_plan && hplan.skip[p]) continue;
       SweepArgs wa{};
       wa.ss = (landing && first_exec) ? ss_in : ss; wa.n = n;
+      const bool was_first = first_exec;
       first_exec = false; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
       wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
@@ -552,11 +580,13 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
         wa.arg_next_skewed = hplan.next_exec_p1[p] ? hplan.skewed[hplan.next_exec_p1[p] - 1] : 0; wa.arg_sub = hplan.sub; wa.arg_lshift = hplan.lshift;
         if (use_fix && hplan.next_exec_p1[p] == 0) { wa.fix_cut = hplan.cut_digit; wa.fix_flag = &ctrl->flags[1]; wa.jtable = (uint64_t *)(ws + L.jtable_off); last_pass = p; }
       }
-      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream));
+      // the first executed pass may rank its keys in any order (nothing has been established yet)
+      const bool unordered = have_plan && was_first && hplan.skewed[p] == 0;
+      CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles, di.smem_optin, di.sm_count, stream, unordered));
     }
-    auto launch_segfix = [&]() -> int {
+    auto launch_segfix = [&](const uint32_t *gate) -> int {
       SegfixArgs fa{};
-      fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl;
+      fa.ss = ss; fa.n = n; fa.ko = ko; fa.plan = plan; fa.ctrl = ctrl; fa.gate = gate;
       if (have_plan) { fa.plan_in_args = 1; fa.arg_cut = hplan.cut_digit; fa.arg_sel = hplan.final_sel; fa.arg_sub = hplan.sub; fa.arg_lshift = hplan.lshift; }
       bool any = false;
       for (int s = 0; s < ss.n_streams; s++) any = any || ss.streams[s].chunk_bytes < 4;
@@ -570,9 +600,9 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       CUDA_TRY(cudaGetLastError());
       return 0;
     };
-    auto launch_copyback = [&](bool force) -> int {
+    auto launch_copyback = [&](bool force, const uint32_t *skip_if) -> int {
       CopyBackArgs ca{};
-      ca.ss = ss; ca.n = n; ca.plan = plan; ca.force = force ? 1 : 0;
+      ca.ss = ss; ca.n = n; ca.plan = plan; ca.force = force ? 1 : 0; ca.skip_if = skip_if;
       {
         ProfScope ps(PK_COPYBACK, stream);
         copyback_kernel<<<di.sm_count * 8, 256, 0, stream>>>(ca);
@@ -581,7 +611,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       CUDA_TRY(cudaGetLastError());
       return 0;
     };
-    bool finish_ran = false;
+    bool finish_ran = false, fix_flow = false;
     if (last_pass >= 0) {
       JunctionArgs ja{};
       ja.ss = ss; ja.n = n; ja.ko = ko; ja.ko.sub = hplan.sub; ja.ko.lshift = hplan.lshift; ja.lookback = lookback; ja.n_tiles = n_tiles;
@@ -594,25 +624,24 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       }
       g_launches++;
       CUDA_TRY(cudaGetLastError());
-      HybridCtrl h1{};
-      CUDA_TRY(cudaMemcpyAsync(&h1, ctrl, sizeof h1, cudaMemcpyDeviceToHost, stream));
-      CUDA_TRY(cudaStreamSynchronize(stream));
-      if (h1.flags[1] != 0) {  // a run too long for the on-the-fly path: the full finish repairs everything
-        if (int rc = launch_segfix()) return rc;
-        finish_ran = true;
-      } else if (hplan.final_sel == 1) {
-        if (int rc = launch_copyback(true)) return rc;
-      }
+      // Both possible continuations are launched; which one does anything is decided on the device by the flag
+      // the last pass / the junction kernel raise when they meet a run that is too long for them: the full
+      // segment finish repairs everything (and delivers the result into the caller's arrays), else the result
+      // is copied out of the shadow if it ended there.  No host round trip in between.
+      if (int rc = launch_segfix(&ctrl->flags[1])) return rc;
+      if (hplan.final_sel == 1)
+        if (int rc = launch_copyback(true, &ctrl->flags[1])) return rc;
+      fix_flow = true;
     } else {
       if (hybrid && !(have_plan && hplan.cut_digit == 0)) {
-        if (int rc = launch_segfix()) return rc;
+        if (int rc = launch_segfix(nullptr)) return rc;
         finish_ran = true;
       }
-      if (int rc = launch_copyback(false)) return rc;
+      if (int rc = launch_copyback(false, nullptr)) return rc;
     }
     stt.passes_planned = (uint32_t)kb;
     stt.hist_sweeps = hist_sweeps;  // probe (+ exact min/max) (+ exact histogram of the first pass)
-    stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
+    stt.algorithmic_bytes = (uint64_t)hist_sweeps * (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
     if (hybrid) {
       // The plan was made on the device; read it (and the fall-back flag) back.  This is the one host
       // synchronisation of the hybrid path.
@@ -620,19 +649,18 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       if (!have_plan) CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaMemcpyAsync(&hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
+      if (fix_flow) finish_ran = hctrl.flags[1] != 0;
       stt.passes_planned = hplan.n_exec;
       stt.segfix_passes = finish_ran ? 1 : 0;
       stt.cut_digit = hplan.cut_digit;
       memcpy(&stt.segfix_moved, &hctrl.flags[2], 8);
-      stt.algorithmic_bytes = 2ull * (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
+      stt.algorithmic_bytes = (uint64_t)hist_sweeps * (uint64_t)n * kb + (uint64_t)(hplan.n_exec + stt.segfix_passes) * 2ull * (uint64_t)n * rec_bytes;
       if (hctrl.flags[0] != 0) {
         // a long bucket with distinct keys: finish with the plain digit-by-digit path (the array is a
         // permutation of the input, already ordered by its top digits)
-        const int64_t saved = opt_algo.exchange(1);
         DevSortOpts fo;
-        fo.layout_n = layout_n; fo.layout_landing = xo.layout_landing;
+        fo.layout_n = layout_n; fo.layout_landing = xo.layout_landing; fo.force_algo = 1;
         const int rc = sort_device(key_type, ascending, n, streams, stream, caller_workspace, workspace_bytes, fo);
-        opt_algo.store(saved);
         if (rc != 0) return rc;
         b200sort_stats s2 = g_last_stats;
         stt.fell_back = 1;
@@ -653,7 +681,23 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
 // ------------------------------------------------------------------------------------------------
 enum Side { SIDE_HOST = 0, SIDE_DEVICE = 1 };
 
-static int side_of(const void *p, Side *out) {
+// makes `dev` the current device for the duration of a call (device arrays are sorted on the device that owns
+// them, whatever the caller's current device is)
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  int enter(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (prev != dev) {
+      if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+      switched = true;
+    }
+    return 0;
+  }
+  ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+};
+
+static int side_of(const void *p, Side *out, int *dev_out = nullptr) {
   cudaPointerAttributes at{};
   cudaError_t e = cudaPointerGetAttributes(&at, p);
   if (e != cudaSuccess) {
@@ -662,6 +706,7 @@ static int side_of(const void *p, Side *out) {
                 cudaGetErrorString(e));
   }
   *out = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? SIDE_DEVICE : SIDE_HOST;
+  if (dev_out) *dev_out = at.device;
   return 0;
 }
 
@@ -848,13 +893,20 @@ static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<S
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   }
   Side side0;
-  if (int rc = side_of(streams[0].ptr, &side0)) return rc;
+  int dev0 = 0;
+  if (int rc = side_of(streams[0].ptr, &side0, &dev0)) return rc;
   for (size_t s = 1; s < streams.size(); s++) {
     Side sd;
-    if (int rc = side_of(streams[s].ptr, &sd)) return rc;
+    int dv = 0;
+    if (int rc = side_of(streams[s].ptr, &sd, &dv)) return rc;
     if (sd != side0) return fail(B200SORT_EINVAL, "arrays must be all in host memory or all in device memory");
+    if (sd == SIDE_DEVICE && dv != dev0) return fail(B200SORT_EINVAL, "device arrays live on different devices (%d and %d)", dev0, dv);
   }
-  if (side0 == SIDE_DEVICE) return sort_device(key_type, ascending, n, streams, stream, workspace, workspace_bytes);
+  if (side0 == SIDE_DEVICE) {
+    DeviceScope scope;  // sort on the device that owns the arrays (include/b200sort.h)
+    if (scope.enter(dev0) != 0) return fail(B200SORT_ECUDA, "cannot make device %d current", dev0);
+    return sort_device(key_type, ascending, n, streams, stream, workspace, workspace_bytes);
+  }
 
   // ---- host arrays, SoA with payloads, big enough to care: pipelined staging --------------------------
   if (opt_host_pipeline.load() != 0 && workspace == nullptr && streams.size() >= 2 &&
@@ -865,7 +917,12 @@ static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<S
     size_t free_b = 0, total_b = 0;
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need < free_b / 10 * 9 + stage_cache_entry(cur_dev).bytes)
+    size_t staged = 0;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      staged = stage_cache_entry(cur_dev).bytes;
+    }
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need < free_b / 10 * 9 + staged)
       return sort_host_pipelined(key_type, ascending, n, streams, stream);
     cudaGetLastError();
   }
@@ -994,7 +1051,9 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!name) return nullptr;
   if (!strcmp(name, "algo")) return &opt_algo;
   if (!strcmp(name, "tile_cfg")) return &opt_tile_cfg;
-  if (!strcmp(name, "use_match")) return &opt_use_match;
+  if (!strcmp(name, "rank_mode")) return &opt_rank_mode;
+  if (!strcmp(name, "first_atomic")) return &opt_first_atomic;
+  if (!strcmp(name, "idx32")) return &opt_idx32;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "allow_reduce")) return &opt_allow_reduce;
   if (!strcmp(name, "spin_ns")) return &opt_spin_ns;

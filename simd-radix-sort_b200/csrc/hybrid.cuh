@@ -43,6 +43,7 @@ struct SegfixArgs {
   uint32_t plan_in_args, arg_cut, arg_sel;
   unsigned long long arg_sub;
   uint32_t arg_lshift;
+  const uint32_t *gate;   // when set: run only if *gate != 0 (the last pass / junction kernel met a run too long for them)
 };
 
 // Moves the queued elements of one chunk column (one warp): entry i goes from window position q_p[i] to
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
   using O = typename OrdOf<KB>::type;
   const uint32_t cut = a.plan_in_args ? a.arg_cut : a.plan->cut_digit;
   if (cut == 0) return;  // every varying digit was swept: nothing to finish
+  if (a.gate != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.gate) == 0) return;  // not needed (decided on the device)
   const uint32_t sel = a.plan_in_args ? a.arg_sel : a.plan->final_sel;
 
   __shared__ O s_wkey[SF_WARPS][SF_W];

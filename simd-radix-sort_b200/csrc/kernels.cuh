@@ -9,6 +9,7 @@
 // order-mapped key (to_ordered(), the closed form of bitDirUp, src/radix_sort.hpp:51-64).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace b200sort {
@@ -139,6 +140,14 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+
+// PRMT: result byte i = byte (sel nibble i & 7) of {a (0..3), b (4..7)}; a nibble with bit 3 set replicates the
+// selected byte's sign bit over the result byte instead
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
 
 // peers of this lane = lanes of the (full) warp holding the same digit
@@ -733,8 +742,8 @@ __device__ __forceinline__ void stage_sync(const unsigned char *src, unsigned ch
 
 // goff[k] is the destination element index of staged slot tid + k*THREADS (computed once per tile,
 // shared by all streams): consecutive threads write consecutive addresses of each bucket.
-template <typename T, int THREADS, int IPT, bool FULL, bool PEER = false>
-__device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const int64_t (&goff)[IPT], int n_valid,
+template <typename T, int THREADS, int IPT, bool FULL, bool PEER = false, typename GOff = int64_t>
+__device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const GOff (&goff)[IPT], int n_valid,
                                           uint32_t cpe, uint32_t c, const int64_t *pdelta = nullptr, const uint32_t *s_prefix = nullptr,
                                           const int64_t *gbase = nullptr, int n_buckets = 0) {
   const T *stage = reinterpret_cast<const T *>(buf) + threadIdx.x;
@@ -766,17 +775,40 @@ __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned cha
   }
 }
 
-template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX, bool FULL>
+// RANK: how a key's position among the tile's keys of the same digit is found
+//   0  eight ballots per row of 32 keys (peer mask from the digit's bits), warp-private counters: stable
+//   1  atomicOr match: lanes OR their lane bit into a per-warp, per-digit word in shared memory and read the
+//      peer mask back (one shared-memory atomic + one load instead of eight votes), warp-private counters: stable
+//   2  one shared-memory atomicAdd per key on per-CTA counters, its return value is the rank: NOT stable --
+//      only for the first executed pass of a sort (its input order carries no information) on a digit whose
+//      histogram is not skewed, full tiles only
+// IDX32: destination indices fit 32 bits (n < 2^32): bucket offsets in shared memory and the per-slot
+// destination offsets are 32-bit (half the registers, one IMAD.WIDE per address).
+constexpr int RANK_BALLOT = 0, RANK_MATCH = 1, RANK_ATOMIC = 2;
+
+template <int THREADS, int RANK>
+__host__ __device__ constexpr size_t sweep_rank_smem_bytes() {
+  // warp-private counters [NWARPS][RADIX] (RANK_ATOMIC uses the first row as the CTA's counters) and, for
+  // RANK_MATCH, two generations of match words per warp
+  return (size_t)(THREADS / 32) * RADIX * 4 * (RANK == RANK_MATCH ? 3 : 1);
+}
+
+template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX, int RANK, bool IDX32, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
                                            const uint32_t sel) {
   constexpr int TILE = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
   using KeyT = typename UIntOf<KB>::type;
+  using GOff = typename std::conditional<IDX32, uint32_t, int64_t>::type;
+  static_assert(FULL || RANK != RANK_ATOMIC, "the padded last tile is ranked by a stable method");
+  static_assert(!(LUT && IDX32), "the partition pass of the multi-GPU sort keeps 64-bit offsets");
 
   unsigned char *stage = smem;                                                               // NSTAGE * TILE * stage_bytes
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)NSTAGE * TILE * a.stage_bytes);  // NWARPS*RADIX
-  int64_t *gbase = reinterpret_cast<int64_t *>(warp_cnt + NWARPS * RADIX);                   // RADIX
-  uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase + RADIX);                          // RADIX
+  uint32_t *warp_match = warp_cnt + NWARPS * RADIX;                                           // RANK_MATCH: 2*NWARPS*RADIX
+  int64_t *gbase64 = reinterpret_cast<int64_t *>(reinterpret_cast<unsigned char *>(warp_cnt) + sweep_rank_smem_bytes<THREADS, RANK>());  // RADIX
+  GOff *gbase = reinterpret_cast<GOff *>(gbase64);                                            // (IDX32: the first half of it)
+  uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase64 + RADIX);                         // RADIX
   uint32_t *s_wsum = s_prefix + RADIX;                                                        // 32
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
   uint8_t *sdigit = reinterpret_cast<uint8_t *>(srank + TILE);                               // TILE
@@ -807,10 +839,21 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   const bool has_sub = ko.sub != 0 || (int)ko.lshift > a.shift;
   static_assert(IPT % 4 == 0, "digits are packed four per register");
   uint32_t dpack[IPT / 4];
+  // 32-bit word of the raw key that holds the (byte-aligned) digit at bit offset es of the key
+  auto word_at = [&](int r, int es) -> uint32_t {
+    if constexpr (KB == 8) return es >= 32 ? (uint32_t)(raw[r] >> 32) : (uint32_t)raw[r];
+    else return (uint32_t)raw[r];
+  };
+  auto top_word = [&](int r) -> uint32_t {  // the word whose byte TOPB carries the sign bit
+    if constexpr (KB == 8) return (uint32_t)(raw[r] >> 32);
+    else return (uint32_t)raw[r];
+  };
+  constexpr uint32_t TOPB = KB == 8 ? 3u : (uint32_t)(KB - 1);
   {
     const DigitX dx = make_digitx(ko, a.shift);
     // padding of the last tile ranks behind everything (digit 255, last in index order)
     auto pad = [&](int r, uint32_t d) -> uint32_t { return (!FULL && idx0 + r * 32 >= n_valid) ? (uint32_t)(RADIX - 1) : d; };
+    const int es = a.shift - (int)ko.lshift;
     if constexpr (LUT) {
 #pragma unroll
       for (int q = 0; q < IPT / 4; q++) {
@@ -829,6 +872,30 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           w |= pad(4 * q + e, (uint32_t)(to_ordered<KB>(raw[4 * q + e], ko) >> a.shift) & (RADIX - 1)) << (8 * e);
         dpack[q] = w;
       }
+    } else if ((es & 7) == 0) {
+      // The common case (no left shift): the digit is one byte of the raw key xor-ed with a constant, so four
+      // digits are gathered into a register by three byte permutes and one xor (+ the sign handling of IEEE keys).
+      const uint32_t bsel = (uint32_t)(es >> 3) & 3u;
+      const uint32_t s2 = bsel | ((4u + bsel) << 4) | 0x4400u;
+      const uint32_t xc4 = dx.xc * 0x01010101u, nx4 = dx.nx * 0x01010101u;
+      constexpr uint32_t SGN2 = (8u + TOPB) | ((12u + TOPB) << 4) | 0x4400u;  // sign bytes of two keys
+#pragma unroll
+      for (int q = 0; q < IPT / 4; q++) {
+        const uint32_t t01 = prmt(word_at(4 * q, es), word_at(4 * q + 1, es), s2);
+        const uint32_t t23 = prmt(word_at(4 * q + 2, es), word_at(4 * q + 3, es), s2);
+        uint32_t w = prmt(t01, t23, 0x5410u) ^ xc4;
+        if (nx4 != 0) {  // IEEE keys: negative keys have their other bits flipped as well
+          const uint32_t m01 = prmt(top_word(4 * q), top_word(4 * q + 1), SGN2);
+          const uint32_t m23 = prmt(top_word(4 * q + 2), top_word(4 * q + 3), SGN2);
+          w ^= prmt(m01, m23, 0x5410u) & nx4;
+        }
+        if constexpr (!FULL) {
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (idx0 + (4 * q + e) * 32 >= n_valid) w |= 0xffu << (8 * e);
+        }
+        dpack[q] = w;
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < IPT / 4; q++) {
@@ -841,20 +908,21 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   }
   auto digit_of = [&](int r) -> uint32_t { return (dpack[r >> 2] >> (8 * (r & 3))) & (RADIX - 1); };
 
-  // ---- rank inside the warp (stable) -----------------------------------------------------------------
+  // ---- rank inside the warp ------------------------------------------------------------------------------
   // ranks (< TILE <= 65536) are kept two to a register: the kernel is at its register limit for 3 CTAs/SM
   uint32_t rankp[IPT / 2];
   auto rank_get = [&](int r) -> uint32_t { return (r & 1) ? (rankp[r >> 1] >> 16) : (rankp[r >> 1] & 0xffffu); };
   auto rank_set = [&](int r, uint32_t v) { rankp[r >> 1] = (r & 1) ? ((rankp[r >> 1] & 0xffffu) | (v << 16)) : ((rankp[r >> 1] & 0xffff0000u) | v); };
 #pragma unroll
   for (int q = 0; q < IPT / 2; q++) rankp[q] = 0;
-  uint32_t *wc = warp_cnt + warp * RADIX;
+  uint32_t *wc = RANK == RANK_ATOMIC ? warp_cnt : warp_cnt + warp * RADIX;
   // the pass executed after this one gets its exact digit histogram from here (keys are in registers)
   const uint32_t next_p1 = LUT ? 0u : (a.plan_in_args ? a.arg_next_p1 : a.plan->next_exec_p1[a.pass]);
   if (next_p1 != 0) {
     const int nshift = (int)(next_p1 - 1) * RADIX_BITS;
     const DigitX dn = make_digitx(ko, nshift);
     const bool skewed = (a.plan_in_args ? a.arg_next_skewed : a.plan->skewed[next_p1 - 1]) != 0;
+    const int esn = nshift - (int)ko.lshift;
     if (has_sub || skewed) {
 #pragma unroll
       for (int r = 0; r < IPT; r++) {
@@ -863,22 +931,56 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         const uint32_t dnext = has_sub ? (uint32_t)(to_ordered<KB>(raw[r], ko) >> nshift) & (RADIX - 1) : fast_digit<KB>(raw[r], dn);
         if (valid) hist_add<false>(nhist, dnext, vmask);
       }
+    } else if ((esn & 7) == 0 && dn.nx == 0) {
+      // byte-aligned digit of an integer key: one byte permute (+ the constant) per key
+      const uint32_t s1 = ((uint32_t)(esn >> 3) & 3u) | 0x4440u;
+#pragma unroll
+      for (int r = 0; r < IPT; r++)
+        if (FULL || idx0 + r * 32 < n_valid) atomicAdd(&nhist[prmt(word_at(r, esn), 0u, s1) ^ dn.xc], 1u);
     } else {
 #pragma unroll
       for (int r = 0; r < IPT; r++)
         if (FULL || idx0 + r * 32 < n_valid) atomicAdd(&nhist[fast_digit<KB>(raw[r], dn)], 1u);
     }
   }
+  if constexpr (RANK == RANK_ATOMIC) {
+    // unstable: the old value of the CTA's counter is the key's rank among the tile's keys of that digit
 #pragma unroll
-  for (int r = 0; r < IPT; r++) {
-    const uint32_t d = digit_of(r);
-    const unsigned peers = digit_peers<false>(d);  // ballots: measured faster than MATCH.ANY on B200
-    const uint32_t cnt = wc[d];
-    __syncwarp();
-    const uint32_t lower = __popc(peers & lanemask_lt());
-    rank_set(r, cnt + lower);
-    if (lower == 0) wc[d] = cnt + __popc(peers);
-    __syncwarp();
+    for (int r = 0; r < IPT; r++) rank_set(r, atomicAdd(&wc[digit_of(r)], 1u));
+  } else if constexpr (RANK == RANK_MATCH) {
+    // Lanes holding digit d OR their lane bit into the warp's word for d; after a warp barrier the word is the
+    // peer mask.  Two generations of words alternate between rows, so that the lowest peer can clear the word
+    // it used while the next row is already filling the other generation.
+    uint32_t *wm = warp_match + warp * (2 * RADIX);
+    const uint32_t lbit = 1u << lane, lt = lanemask_lt();
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const uint32_t d = digit_of(r);
+      uint32_t *m = wm + (r & 1) * RADIX + d;
+      atomicOr(m, lbit);
+      __syncwarp();
+      const uint32_t peers = *m;
+      const uint32_t cnt = wc[d];
+      __syncwarp();
+      const uint32_t lower = __popc(peers & lt);
+      rank_set(r, cnt + lower);
+      if (lower == 0) {
+        wc[d] = cnt + __popc(peers);
+        *m = 0;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const uint32_t d = digit_of(r);
+      const unsigned peers = digit_peers<false>(d);
+      const uint32_t cnt = wc[d];
+      __syncwarp();
+      const uint32_t lower = __popc(peers & lanemask_lt());
+      rank_set(r, cnt + lower);
+      if (lower == 0) wc[d] = cnt + __popc(peers);
+      __syncwarp();
+    }
   }
   __syncthreads();
 
@@ -890,11 +992,15 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       if (c) atomicAdd(reinterpret_cast<unsigned long long *>(&a.ghist[(size_t)(next_p1 - 1) * RADIX + tid]), (unsigned long long)c);
     }
     uint32_t run = 0;
+    if constexpr (RANK == RANK_ATOMIC) {
+      run = warp_cnt[tid];
+    } else {
 #pragma unroll
-    for (int w = 0; w < NWARPS; w++) {
-      const uint32_t t = warp_cnt[w * RADIX + tid];
-      warp_cnt[w * RADIX + tid] = run;
-      run += t;
+      for (int w = 0; w < NWARPS; w++) {
+        const uint32_t t = warp_cnt[w * RADIX + tid];
+        warp_cnt[w * RADIX + tid] = run;
+        run += t;
+      }
     }
     my_count = run;
     uint32_t inc = run;
@@ -919,13 +1025,13 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         const uint64_t v = __shfl_up_sync(0xffffffffu, t0_inc, o);
         if (lane >= o) t0_inc += v;
       }
-      if (lane == 31) gbase[warp] = (int64_t)t0_inc;  // gbase is free until the look-back
+      if (lane == 31) gbase64[warp] = (int64_t)t0_inc;  // gbase is free until the look-back
     }
   }
   __syncthreads();
   if (tile == 0 && tid < RADIX && a.bin_base == nullptr) {
     uint64_t off = 0;
-    for (int w = 0; w < warp; w++) off += (uint64_t)gbase[w];
+    for (int w = 0; w < warp; w++) off += (uint64_t)gbase64[w];
     tile0_base = off + t0_inc - t0_cnt;
   }
   const uint64_t tagbits = (uint64_t)a.tag << LB_TAG_SHIFT;
@@ -949,7 +1055,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
     const uint32_t d = digit_of(r);
-    const uint32_t rk = rank_get(r) + s_prefix[d] + wc[d];
+    const uint32_t rk = RANK == RANK_ATOMIC ? rank_get(r) + s_prefix[d] : rank_get(r) + s_prefix[d] + wc[d];
     rank_set(r, rk);
     sdigit[rk] = (uint8_t)d;
     srank[idx0 + r * 32] = (uint16_t)rk;  // payload streams pick their slot up from here
@@ -1025,7 +1131,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       }
       st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
     }
-    gbase[tid] = (int64_t)excl - (int64_t)s_prefix[tid];
+    gbase[tid] = (GOff)excl - (GOff)s_prefix[tid];  // (32-bit: wraps, the slot index added later brings it back)
   }
   if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
   __shared__ uint32_t s_given_up;
@@ -1057,7 +1163,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       // lane l starting at window position l mod W: a warp's loads then spread over the banks although the
       // threads' windows are IPT keys apart.  (Equal swept bits of the ordered keys <=> equal swept bits of
       // the raw keys: the order mapping is an xor whose only key-dependent part is the sign bit, itself a
-      // swept bit, and no range reduction is active when a cut exists.  Sentinel 1 never equals a masked key.)
+      // swept bit, and no range reduction is active when a cut exists.  Slots outside the tile are masked below.)
       // once any tile has met a run that is too long, the full segment finish is going to run anyway: the
       // tiles after it do not bother (keys with many duplicates would otherwise pay for nothing).  The whole
       // tile takes the same decision: the members of a run must all apply their displacement, or none.
@@ -1086,6 +1192,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         if (KB == 8 && cut_bit >= 32) scan_window((uint32_t)0); else scan_window((O)0);
         // re-index by window position: bit j = slots (base-1+j, base+j) agree, j = 0 .. IPT; bit W-1 is the wrap
         eq = ((eq << rot) | (eq >> (W - rot))) & ((1u << (W - 1)) - 1u);
+        // Window positions outside the tile ([0, lim)) hold no key: a pair that involves one never agrees,
+        // whatever the placeholder compared equal to (a real key's swept bits may well be 0x...01, e.g. a raw
+        // high word of 1 under a 32-bit cut).  Bit j pairs slots (base-1+j, base+j).
+        if (base == 0) eq &= ~1u;
+        if (lim - base <= IPT) eq &= (1u << max(lim - base, 0)) - 1u;
         uint32_t members = (eq | (eq >> 1)) & ((1u << IPT) - 1u);  // own slots with an equal neighbour
         if (!FULL) members &= lim - base >= IPT ? ~0u : (1u << max(lim - base, 0)) - 1u;  // sentinels are no members
         // Exact pairs that lie inside the own slots and whose surroundings are known from the window (four runs
@@ -1167,11 +1278,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     }
   }
 
-  int64_t goff[IPT];
+  GOff goff[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     const int i = tid + k * THREADS;
-    goff[k] = (FULL || i < n_valid) ? gbase[sdigit[i]] + i + (FIX ? (int)sdelta[i] : 0) : 0;
+    goff[k] = (FULL || i < n_valid) ? (GOff)(gbase[sdigit[i]] + (GOff)(i + (FIX ? (int)sdelta[i] : 0))) : (GOff)0;
   }
   int wr_s = 0;  // write cursor
   uint32_t wr_c = 0;
@@ -1181,11 +1292,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       unsigned char *dst = st.buf[sel ^ 1];
       const unsigned char *buf = bufs[NSTAGE == 2 ? (j & 1) : 0];
       const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
-      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
-      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
-      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
-      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
-      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase, a.lut_world);
+      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
+      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
+      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
+      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
+      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
       if (++wr_c == cpe) { wr_c = 0; wr_s++; }
     }
     if (wr_s >= a.ss.n_streams) break;
@@ -1205,7 +1316,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
 // ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
 // far more registers per thread, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX = false>
+template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX = false, int RANK = RANK_BALLOT, bool IDX32 = false>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
@@ -1215,21 +1326,23 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
 
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * TILE * a.stage_bytes);
-  uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + NWARPS * RADIX) + RADIX * 8);  // = s_prefix
+  constexpr int RANK_WORDS = (int)(sweep_rank_smem_bytes<THREADS, RANK>() / 4);
+  uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + RANK_WORDS) + RADIX * 8);  // = s_prefix
   // One tile per CTA.  (A persistent grid that loops over tickets was measured 17 % slower: CTAs that
   // start together stay in phase, so loads, look-backs and stores of the whole machine bunch up; fresh
   // CTAs per tile stagger naturally.  profiles/README.md)
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
-  for (int i = threadIdx.x; i < NWARPS * RADIX / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
+  // (RANK_ATOMIC only needs the CTA's one row of counters; the padded last tile uses the warps' rows)
+  for (int i = threadIdx.x; i < RANK_WORDS / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
   if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, true>(a, smem, tile, TILE, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK, IDX32, true>(a, smem, tile, TILE, sel);
   else
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, false>(a, smem, tile, (int)remaining, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK == RANK_ATOMIC ? RANK_BALLOT : RANK, IDX32, false>(a, smem, tile, (int)remaining, sel);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1240,10 +1353,12 @@ struct CopyBackArgs {
   int64_t n;
   const Plan *plan;
   int force;  // 1: the host knows the result is in the shadow (no finish kernel delivered it)
+  const uint32_t *skip_if;  // when set: do nothing if *skip_if != 0 (the segment finish ran and delivered the result)
 };
 
 static __global__ void __launch_bounds__(256) copyback_kernel(const __grid_constant__ CopyBackArgs a) {
   if (!a.force && (a.plan->final_sel == 0 || a.plan->cut_digit != 0)) return;  // (the segment finish already wrote side 0)
+  if (a.skip_if != nullptr && *reinterpret_cast<const volatile uint32_t *>(a.skip_if) != 0) return;
   for (int s = 0; s < a.ss.n_streams; s++) {
     const Stream &st = a.ss.streams[s];
     const size_t bytes = (size_t)a.n * st.chunk_bytes * st.chunks_per_elem;

@@ -487,6 +487,8 @@ int b200sort_mgpu_sort_soa(b200sort_comm *c, void *keys, int key_type, int64_t n
   const int world = c->world;
   const int bits = std::min(MGPU_MAX_BITS, 8 * kb);
   const uint32_t nb = 1u << bits;
+  DeviceScope dev_scope;  // the communicator's device, whatever the caller's current device is
+  if (dev_scope.enter(c->dev) != 0) return fail(B200SORT_ECUDA, "cannot make device %d current", c->dev);
   DevInfo di;
   if (int rc = dev_info(c->dev, &di)) return rc;
   const KeyOrder ko = make_key_order(key_type, ascending != 0);

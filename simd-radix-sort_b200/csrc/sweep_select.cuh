@@ -1,6 +1,7 @@
-// sweep_select.cuh -- maps (key bytes, tile geometry, staging depth, chunk widths) to an instantiation of
-// onesweep_kernel.  The instantiations of each key width live in their own translation unit
-// (sweep_kb{1,2,4,8}.cu) so that they compile in parallel.
+// sweep_select.cuh -- maps (key bytes, tile geometry, staging depth, chunk widths, ranking method, index
+// width) to an instantiation of onesweep_kernel.  The instantiations of each (key width, geometry) pair
+// live in their own translation unit (sweep_inst.cu compiled with -DSWEEP_KB=.. -DSWEEP_CFG=..) so that
+// they compile in parallel.
 #pragma once
 #include "kernels.cuh"
 
@@ -9,34 +10,42 @@ namespace b200sort {
 using SweepFn = void (*)(const SweepArgs);
 
 struct TileCfg { int threads, ipt, minb; };
-// tile geometries of the scatter kernel (option "tile_cfg"); minb = CTAs per SM the kernel is compiled for
-constexpr TileCfg kTileCfgs[] = {{512, 16, 1}, {256, 16, 3}, {256, 8, 4}, {256, 16, 4}};
+// tile geometries of the scatter kernel (option "tile_cfg"); minb = CTAs per SM the kernel is compiled for.
+// (512x16x1 and 256x16x4 were measured slower in round 1 and are gone: profiles/README.md)
+constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}};
 constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
+constexpr int kDefaultTileCfg = 0;
+
+struct SweepSel {
+  int nstage;   // 1 or 2 staging buffers
+  bool any;     // a stream with 1- or 2-byte chunks takes part
+  bool lut;     // partition pass of the multi-GPU sort
+  bool fix;     // last pass of the MSB hybrid plan (8-byte keys, default geometry)
+  int rank;     // RANK_BALLOT / RANK_MATCH / RANK_ATOMIC
+  bool idx32;   // n < 2^32
+};
+
+template <int KB, int THREADS, int IPT, int MINB, int RANK, bool IDX32>
+inline SweepFn sweep_variant2(const SweepSel &s) {
+  if constexpr (KB == 8 && THREADS == 256 && IPT == 16 && RANK != RANK_ATOMIC) {
+    if (s.fix) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, true, RANK, IDX32> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, true, RANK, IDX32>;
+  }
+  if (s.nstage == 2) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true, false, false, RANK, IDX32> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false, false, false, RANK, IDX32>;
+  return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, false, RANK, IDX32> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, false, RANK, IDX32>;
+}
 
 template <int KB, int THREADS, int IPT, int MINB>
-inline SweepFn sweep_variant(int nstage, bool any, bool lut, bool fix) {
-  if (lut) return onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true>;  // multi-GPU partition pass
-  if constexpr (KB == 8 && THREADS == 256 && IPT == 16 && MINB == 3) {
-    // last pass of the MSB hybrid plan (8-byte keys, default geometry): orders the final segments a tile holds
-    if (fix) return any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, true> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, true>;
-  }
-  if (nstage == 2) return any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false, false>;
-  return any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false>;
+inline SweepFn sweep_variant(const SweepSel &s) {
+  if (s.lut) return s.rank == RANK_BALLOT ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true, false, RANK_BALLOT, false>
+                                          : onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true, false, RANK_MATCH, false>;
+  if (s.rank == RANK_ATOMIC && !s.fix) return s.idx32 ? sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, true>(s) : sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, false>(s);
+  if (s.rank == RANK_BALLOT) return s.idx32 ? sweep_variant2<KB, THREADS, IPT, MINB, RANK_BALLOT, true>(s) : sweep_variant2<KB, THREADS, IPT, MINB, RANK_BALLOT, false>(s);
+  return s.idx32 ? sweep_variant2<KB, THREADS, IPT, MINB, RANK_MATCH, true>(s) : sweep_variant2<KB, THREADS, IPT, MINB, RANK_MATCH, false>(s);
 }
 
-template <int KB>
-inline SweepFn sweep_fn(int cfg, int nstage, bool any, bool lut, bool fix) {
-  switch (cfg) {
-    case 0: return sweep_variant<KB, 512, 16, 1>(nstage, any, lut, fix);
-    case 1: return sweep_variant<KB, 256, 16, 3>(nstage, any, lut, fix);
-    case 2: return sweep_variant<KB, 256, 8, 4>(nstage, any, lut, fix);
-    default: return sweep_variant<KB, 256, 16, 4>(nstage, any, lut, fix);
-  }
-}
+// defined in sweep_inst.cu, one translation unit per (key bytes, geometry)
+template <int KB, int CFG> SweepFn sweep_fn_inst(const SweepSel &s);
 
-SweepFn sweep_fn_kb1(int cfg, int nstage, bool any, bool lut, bool fix);
-SweepFn sweep_fn_kb2(int cfg, int nstage, bool any, bool lut, bool fix);
-SweepFn sweep_fn_kb4(int cfg, int nstage, bool any, bool lut, bool fix);
-SweepFn sweep_fn_kb8(int cfg, int nstage, bool any, bool lut, bool fix);
+inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s);
 
 }  // namespace b200sort

@@ -282,3 +282,39 @@ def make_records(keys: np.ndarray, record_bytes: int) -> np.ndarray:
         port().oracle_make_payloads(keys_c.ctypes.data, kb, n, 1, ptrs, sizes)
         rec[:, kb:] = flat.reshape(n, -1)
     return rec
+
+
+# ---------------------------------------------------------------------------------------------------
+# counter-based key generator shared by host (numpy) and device (torch) code: key i = mix64(seed + i)
+# (splitmix64 finaliser; the same function sortbench.cu and bench.py use), so that both arms of a
+# comparison sort the very same records without shipping them.
+# ---------------------------------------------------------------------------------------------------
+_M1, _M2, _M3 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+
+
+def mix64_numpy(start: int, count: int, seed: int) -> np.ndarray:
+    """uint64 keys mix64(seed + i) for i in [start, start + count)"""
+    with np.errstate(over="ignore"):
+        x = np.arange(start, start + count, dtype=np.uint64) + np.uint64(seed % (1 << 64))
+        x = x + np.uint64(_M1)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(_M2)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(_M3)
+        return x ^ (x >> np.uint64(31))
+
+
+def mix64_torch(start: int, count: int, seed: int, device):
+    """the same keys on a torch device, as an int64 tensor holding the uint64 bit patterns"""
+    import torch
+
+    def s64(v):  # python int -> the int64 with the same low 64 bits
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(t, s):
+        return (t >> s) & ((1 << (64 - s)) - 1)
+
+    x = torch.arange(start, start + count, dtype=torch.int64, device=device) + s64(seed)
+    x = x + s64(_M1)
+    x = (x ^ lsr(x, 30)) * s64(_M2)
+    x = (x ^ lsr(x, 27)) * s64(_M3)
+    return x ^ lsr(x, 31)

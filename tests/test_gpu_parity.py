@@ -220,20 +220,87 @@ def test_large_properties(case):
 
 
 def test_tile_geometries_and_ranking_variants_agree():
+    """both tile geometries x the two stable ranking methods (ballots / atomicOr match) x 32-/64-bit offsets"""
     n = 300_000
     keys = O.make_keys("Uniform", np.uint64, n, seed=77)
     want = np.sort(keys)
     try:
-        for cfg in range(4):
-            for use_match in (0, 1):
-                S.set_option("tile_cfg", cfg)
-                S.set_option("use_match", use_match)
-                k, (p,) = gpu_sort_soa(keys, [np.arange(n, dtype=np.uint32)], True)
-                assert k.tobytes() == want.tobytes(), (cfg, use_match)
-                assert keys[p].tobytes() == k.tobytes(), (cfg, use_match)
+        for cfg in range(2):
+            for rank_mode in (0, 1):
+                for idx32 in (0, 1):
+                    S.set_option("tile_cfg", cfg)
+                    S.set_option("rank_mode", rank_mode)
+                    S.set_option("idx32", idx32)
+                    k, (p,) = gpu_sort_soa(keys, [np.arange(n, dtype=np.uint32)], True)
+                    assert k.tobytes() == want.tobytes(), (cfg, rank_mode, idx32)
+                    assert keys[p].tobytes() == k.tobytes(), (cfg, rank_mode, idx32)
     finally:
         S.set_option("tile_cfg", -1)
-        S.set_option("use_match", 1)
+        S.set_option("rank_mode", 1)
+        S.set_option("idx32", 1)
+
+
+@pytest.mark.parametrize("first_atomic", [0, 1])
+def test_unstable_first_pass_ranking(first_atomic):
+    """large-sort flow: the first executed pass may rank with one shared-memory atomic per key (unstable);
+    every later pass stays stable -- same result either way, payloads follow their keys"""
+    n = (1 << 20) + 4099
+    rng = np.random.default_rng(5 + first_atomic)
+    try:
+        S.set_option("host_plan_min_log2", 0)
+        S.set_option("first_atomic", first_atomic)
+        S.set_option("algo", 2)
+        for dt in (np.uint64, np.int64, np.float64):
+            keys = O.make_keys("Uniform", dt, n, seed=21)
+            keys[::11] = keys[5]  # duplicates of one value
+            for up in (True, False):
+                idx = np.arange(n, dtype=np.uint64)
+                k, (p,) = gpu_sort_soa(keys, [idx], up)
+                assert k.tobytes() == O.total_order_sorted_keys(keys, up).tobytes(), (dt, up)
+                assert np.array_equal(np.sort(p), idx) and keys[p.astype(np.int64)].tobytes() == k.tobytes(), (dt, up)
+    finally:
+        S.set_option("host_plan_min_log2", 24)
+        S.set_option("first_atomic", 1)
+        S.set_option("algo", 0)
+
+
+@pytest.mark.parametrize("up", [True, False])
+def test_last_pass_window_at_tile_edges_with_32_bit_cut(up):
+    """with the cut at bit 32 the swept bits are the raw high word; a key whose high word is 1
+    sits in the first (ascending) / last (descending) slot of its tile, where the window of the tile-local
+    ordering looks one slot outside the tile.  Slots outside the tile must never pair with a key."""
+    n = (1 << 20) + 4099
+    rng = np.random.default_rng(32)
+    try:
+        S.set_option("algo", 2)
+        S.set_option("host_plan_min_log2", 0)
+        S.set_option("margin_bits", 12)   # log2(n) + 12 = 32 swept bits: cut digit 4
+        hi = rng.integers(0, 2**32, size=n, dtype=np.uint64)
+        # plenty of keys with raw high word 1 (and 0, 2: neighbours), in runs so that they also meet in one tile
+        hi[rng.integers(0, n, size=n // 8)] = 1
+        hi[rng.integers(0, n, size=n // 16)] = 0
+        hi[rng.integers(0, n, size=n // 16)] = 2
+        lo = rng.integers(0, 2**32, size=n, dtype=np.uint64)
+        keys = (hi << np.uint64(32)) | lo
+        idx = np.arange(n, dtype=np.uint32)
+        for dt in (np.uint64, np.int64):
+            kk = np.ascontiguousarray(keys.view(dt))
+            k, (p,) = gpu_sort_soa(kk, [idx], up)
+            st = S.last_stats()
+            assert st["algo"] == 2
+            assert k.tobytes() == O.total_order_sorted_keys(kk, up).tobytes(), (dt, up)
+            assert np.array_equal(np.sort(p), idx) and kk[p].tobytes() == k.tobytes(), (dt, up)
+        # sparse version: exactly the edge keys, unique low words (cut digit 4 is checked)
+        keys2 = (rng.integers(0, 2**32, size=n, dtype=np.uint64) << np.uint64(32)) | lo
+        keys2[:4096] = (np.uint64(1) << np.uint64(32)) | np.arange(4096, dtype=np.uint64)[::-1]
+        k, (p,) = gpu_sort_soa(keys2, [idx], up)
+        assert S.last_stats()["cut_digit"] == 4, S.last_stats()
+        assert k.tobytes() == O.total_order_sorted_keys(keys2, up).tobytes()
+        assert kk is not None and keys2[p].tobytes() == k.tobytes()
+    finally:
+        S.set_option("algo", 0)
+        S.set_option("host_plan_min_log2", 24)
+        S.set_option("margin_bits", 2)
 
 
 def test_caller_workspace_and_stats():
