@@ -122,19 +122,20 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // tile geometries of the scatter kernel
 // ------------------------------------------------------------------------------------------------
-static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false, bool lut = false, int rank = RANK_MATCH) {
+static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstage = 1, bool fix = false, bool lut = false) {
   const size_t tile = (size_t)c.threads * c.ipt;
-  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 * (rank == RANK_MATCH ? 3 : 1) + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 +
+  return (size_t)nstage * tile * stage_bytes + (size_t)(c.threads / 32) * RADIX * 4 + RADIX * 8 + RADIX * 4 + 32 * 4 + tile * 3 +
          (fix ? tile : 0) +       // FIX: per-slot displacement
          (lut ? RADIX * 8 : 0);   // LUT: peer byte offsets
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
-static std::atomic<int64_t> opt_rank_mode{1};     // stable ranking: 0 ballots, 1 atomicOr match
+static std::atomic<int64_t> opt_tma_keys{1};      // key tiles arrive by one TMA bulk copy per tile (cp.async.bulk + mbarrier)
+static std::atomic<int64_t> opt_bytewise{1};      // lean kernels when the host knows the plan (no range reduction / shift)
 static std::atomic<int64_t> opt_first_atomic{1};  // first executed pass of a large sort: unstable atomicAdd ranking
-static std::atomic<int64_t> opt_idx32{1};         // 32-bit destination offsets when n < 2^32
 
 inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
+  if (cfg == 2 && kb != 8) cfg = 0;
   switch (kb * 2 + cfg) {
     case 2: return sweep_fn_inst<1, 0>(s);
     case 3: return sweep_fn_inst<1, 1>(s);
@@ -143,7 +144,8 @@ inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
     case 8: return sweep_fn_inst<4, 0>(s);
     case 9: return sweep_fn_inst<4, 1>(s);
     case 16: return sweep_fn_inst<8, 0>(s);
-    default: return sweep_fn_inst<8, 1>(s);
+    case 17: return sweep_fn_inst<8, 1>(s);
+    default: return sweep_fn_inst<8, 2>(s);  // (experimental geometry, 8-byte keys only)
   }
 }
 
@@ -162,22 +164,28 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   const TileCfg tc = kTileCfgs[cfg];
   const bool lut = a.lut != nullptr;
   const bool fix = !lut && a.fix_cut != 0;  // (the caller only sets fix_cut where the FIX instantiation exists)
-  int rank = opt_rank_mode.load() != 0 ? RANK_MATCH : RANK_BALLOT;
-  if (first_pass_unordered && !lut && !fix && opt_first_atomic.load() != 0) rank = RANK_ATOMIC;
+  int rank = RANK_BALLOT;
+  // digits are whole bytes of the raw key when the host knows that the plan has no range reduction and no shift
+  const bool bytewise = !lut && a.plan_in_args != 0 && a.arg_sub == 0 && a.arg_lshift == 0 && opt_bytewise.load() != 0;
+  if (first_pass_unordered && bytewise && !fix && opt_first_atomic.load() != 0) rank = RANK_ATOMIC;
   // double-buffer the columns when there is more than one and minb CTAs still fit on an SM
   int nstage = (int)opt_nstage.load();
   if (nstage != 1 && nstage != 2)
-    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2, false, false, rank) + 1024) * tc.minb <= smem_optin + 1024) ? 2 : 1;
-  if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2, false, false, rank) > smem_optin) nstage = 1;
+    nstage = (n_cols >= 2 && (sweep_smem_bytes(tc, a.stage_bytes, 2) + 1024) * tc.minb <= smem_optin + 1024) ? 2 : 1;
+  if (nstage == 2 && sweep_smem_bytes(tc, a.stage_bytes, 2) > smem_optin) nstage = 1;
   if (lut || fix) nstage = 1;
-  SweepSel sel{nstage, any || lut, lut, fix, rank, !lut && opt_idx32.load() != 0 && a.n < ((int64_t)1 << 32)};
+  SweepSel sel{nstage, any || lut, lut, fix, rank, bytewise};
+  SweepArgs a2 = a;
+  // TMA bulk load of the key tile: SoA keys whose arrays (both sides of the ping-pong) are 16-byte aligned
+  a2.tma_keys = (opt_tma_keys.load() != 0 && soa && (((uintptr_t)a.ss.streams[0].buf[0] | (uintptr_t)a.ss.streams[0].buf[1]) & 15) == 0 &&
+                 ((size_t)tc.threads * tc.ipt * kb) % 16 == 0) ? 1u : 0u;
   SweepFn k = sweep_fn(kb, cfg, sel);
-  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut, rank);
+  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
   (void)sm_count;
-  k<<<(unsigned)n_tiles, tc.threads, smem, st>>>(a);
+  k<<<(unsigned)n_tiles, tc.threads, smem, st>>>(a2);
   g_launches++;
   return cudaGetLastError();
 }
@@ -449,7 +457,9 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     //      scatter pass per digit position (skipped ones return at once), segment finish, copy-back ----
     uint64_t *ghist_exact = (uint64_t *)(ws + L.ghist2_off);
     ProbeOut *probe = (ProbeOut *)(ws + L.probe_off);
-    const bool big = hybrid && n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);  // the host reads the plan back
+    // large sorts (any algorithm): the host reads the plan back and launches exactly what executes, with the
+    // plan's values as kernel arguments and the lean kernel instantiations they allow
+    const bool big = n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);
     // Input in the landing arrays (multi-GPU): only the large hybrid flow knows on the host which pass runs
     // first; everything else simply starts with a copy into the caller's arrays.
     bool landing = xo.landing_input;
@@ -491,6 +501,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
         const int cut = 8 - hint_lead_bits / 8 - swept;
         if (cut >= 2) { guess = (uint32_t)cut; guess_l = (uint32_t)shift_l; }
       }
+      // (digit-by-digit path: the least significant digit, guess = 0, is the first pass unless it is constant)
       ha.guess_lshift = guess_l;
       ha.guess_p1 = opt_probe_guess.load() != 0 ? guess + 1 : 0;
       ha.ghist_exact = ghist_exact;
@@ -642,6 +653,10 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     stt.passes_planned = (uint32_t)kb;
     stt.hist_sweeps = hist_sweeps;  // probe (+ exact min/max) (+ exact histogram of the first pass)
     stt.algorithmic_bytes = (uint64_t)hist_sweeps * (uint64_t)n * kb + (uint64_t)kb * 2ull * (uint64_t)n * rec_bytes;
+    if (have_plan) {  // the executed passes are known
+      stt.passes_planned = hplan.n_exec;
+      stt.algorithmic_bytes = (uint64_t)hist_sweeps * (uint64_t)n * kb + (uint64_t)hplan.n_exec * 2ull * (uint64_t)n * rec_bytes;
+    }
     if (hybrid) {
       // The plan was made on the device; read it (and the fall-back flag) back.  This is the one host
       // synchronisation of the hybrid path.
@@ -1051,9 +1066,9 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!name) return nullptr;
   if (!strcmp(name, "algo")) return &opt_algo;
   if (!strcmp(name, "tile_cfg")) return &opt_tile_cfg;
-  if (!strcmp(name, "rank_mode")) return &opt_rank_mode;
   if (!strcmp(name, "first_atomic")) return &opt_first_atomic;
-  if (!strcmp(name, "idx32")) return &opt_idx32;
+  if (!strcmp(name, "tma_keys")) return &opt_tma_keys;
+  if (!strcmp(name, "bytewise")) return &opt_bytewise;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "allow_reduce")) return &opt_allow_reduce;
   if (!strcmp(name, "spin_ns")) return &opt_spin_ns;

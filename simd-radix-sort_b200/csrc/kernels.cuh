@@ -166,6 +166,39 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d) {
   }
 }
 
+// The same for the digit in byte BYTE of a register that packs four digits.  Per bit: one LOP3 that tests the
+// bit straight into a predicate, the vote, one select and one 3-input LOP3 -- written out in PTX because the
+// compiler otherwise extracts every bit twice (shift, mask, compare for the vote; test, select for the mask:
+// seven instructions per bit, the largest single item of the scatter pass's instruction count in round 1).
+template <uint32_t MASK>
+__device__ __forceinline__ void peer_step(unsigned &peers, uint32_t word) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 t, bal, m;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+      "selp.b32 m, 0xffffffff, 0, p;\n\t"
+      "lop3.b32 %0, %0, bal, m, 0x90;\n\t"  // peers & ~(bal ^ m): bal where my bit is set, ~bal where it is clear
+      "}"
+      : "+r"(peers)
+      : "r"(word), "n"(MASK));
+}
+template <int BYTE>
+__device__ __forceinline__ unsigned packed_digit_peers(uint32_t word) {
+  unsigned peers = 0xffffffffu;
+  peer_step<1u << (8 * BYTE + 0)>(peers, word);
+  peer_step<1u << (8 * BYTE + 1)>(peers, word);
+  peer_step<1u << (8 * BYTE + 2)>(peers, word);
+  peer_step<1u << (8 * BYTE + 3)>(peers, word);
+  peer_step<1u << (8 * BYTE + 4)>(peers, word);
+  peer_step<1u << (8 * BYTE + 5)>(peers, word);
+  peer_step<1u << (8 * BYTE + 6)>(peers, word);
+  peer_step<1u << (8 * BYTE + 7)>(peers, word);
+  return peers;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: digit histograms of every digit position in one sweep over the keys.
 // Warp-aggregated shared-memory counters: lanes holding the same digit elect one lane that adds the
@@ -649,6 +682,9 @@ struct SweepArgs {
   uint32_t arg_lshift;
   // FIX instantiation (last pass of the MSB hybrid plan): Plan::cut_digit and where to report a run of
   // more than FIX_CAP keys that agree on all swept bits (the full segment finish then has to run)
+  // the key tile of a full tile arrives by one TMA bulk copy (SoA keys, 16-byte aligned arrays), issued by the
+  // kernel's first thread right after it has drawn the tile ticket
+  uint32_t tma_keys;
   uint32_t fix_cut;
   uint32_t *fix_flag;
   // ... and [n_tiles][RADIX] words {fingerprint of the swept bits of the first key | of the last key << 32} of
@@ -711,6 +747,36 @@ __device__ __forceinline__ void cp_async(uint32_t smem_addr, const void *gptr) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous key tile into shared memory -------------
+// One elected thread arms an mbarrier with the tile's byte count and issues ONE bulk copy for the whole tile
+// (32 KB for 4096 8-byte keys); every thread then waits on the barrier's phase and picks its keys up from
+// shared memory.  Replaces IPT global loads (+ their address arithmetic) per thread.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(b), "r"(parity)
+        : "memory");
+  }
+}
 
 template <int CB, int IPT, bool FULL>
 __device__ __forceinline__ void stage_async(const unsigned char *src, unsigned char *buf, const uint16_t *srank, int64_t tile_base,
@@ -776,38 +842,30 @@ __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned cha
 }
 
 // RANK: how a key's position among the tile's keys of the same digit is found
-//   0  eight ballots per row of 32 keys (peer mask from the digit's bits), warp-private counters: stable
-//   1  atomicOr match: lanes OR their lane bit into a per-warp, per-digit word in shared memory and read the
-//      peer mask back (one shared-memory atomic + one load instead of eight votes), warp-private counters: stable
-//   2  one shared-memory atomicAdd per key on per-CTA counters, its return value is the rank: NOT stable --
-//      only for the first executed pass of a sort (its input order carries no information) on a digit whose
-//      histogram is not skewed, full tiles only
-// IDX32: destination indices fit 32 bits (n < 2^32): bucket offsets in shared memory and the per-slot
-// destination offsets are 32-bit (half the registers, one IMAD.WIDE per address).
-constexpr int RANK_BALLOT = 0, RANK_MATCH = 1, RANK_ATOMIC = 2;
+//   RANK_BALLOT  eight ballots per row of 32 keys (peer mask from the digit's bits), warp-private counters:
+//                stable
+//   RANK_ATOMIC  one shared-memory atomicAdd per key on per-CTA counters, its return value is the rank: NOT
+//                stable -- only for the first executed pass of a sort (its input order carries no information)
+//                on a digit whose histogram is not skewed, full tiles only (-12 % on that pass)
+// (An atomicOr-match ranking -- lanes OR their lane bit into a per-warp, per-digit shared-memory word and read
+//  the peer mask back -- was measured 7 % SLOWER than the ballots at 1e9 records, and 32-bit destination
+//  offsets 4 % slower than 64-bit ones: profiles/README.md, round 2.  Both are gone.)
+constexpr int RANK_BALLOT = 0, RANK_ATOMIC = 2;
 
-template <int THREADS, int RANK>
-__host__ __device__ constexpr size_t sweep_rank_smem_bytes() {
-  // warp-private counters [NWARPS][RADIX] (RANK_ATOMIC uses the first row as the CTA's counters) and, for
-  // RANK_MATCH, two generations of match words per warp
-  return (size_t)(THREADS / 32) * RADIX * 4 * (RANK == RANK_MATCH ? 3 : 1);
-}
-
-template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX, int RANK, bool IDX32, bool FULL>
+template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX, int RANK, bool BYTEWISE, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
-                                           const uint32_t sel) {
+                                           const uint32_t sel, uint64_t *key_bar) {
   constexpr int TILE = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
   using KeyT = typename UIntOf<KB>::type;
-  using GOff = typename std::conditional<IDX32, uint32_t, int64_t>::type;
+  using GOff = int64_t;
   static_assert(FULL || RANK != RANK_ATOMIC, "the padded last tile is ranked by a stable method");
-  static_assert(!(LUT && IDX32), "the partition pass of the multi-GPU sort keeps 64-bit offsets");
+  static_assert(!(LUT && BYTEWISE), "the partition pass's digit is a table look-up");
 
   unsigned char *stage = smem;                                                               // NSTAGE * TILE * stage_bytes
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(stage + (size_t)NSTAGE * TILE * a.stage_bytes);  // NWARPS*RADIX
-  uint32_t *warp_match = warp_cnt + NWARPS * RADIX;                                           // RANK_MATCH: 2*NWARPS*RADIX
-  int64_t *gbase64 = reinterpret_cast<int64_t *>(reinterpret_cast<unsigned char *>(warp_cnt) + sweep_rank_smem_bytes<THREADS, RANK>());  // RADIX
-  GOff *gbase = reinterpret_cast<GOff *>(gbase64);                                            // (IDX32: the first half of it)
+  int64_t *gbase64 = reinterpret_cast<int64_t *>(warp_cnt + NWARPS * RADIX);                   // RADIX
+  GOff *gbase = gbase64;
   uint32_t *s_prefix = reinterpret_cast<uint32_t *>(gbase64 + RADIX);                         // RADIX
   uint32_t *s_wsum = s_prefix + RADIX;                                                        // 32
   uint16_t *srank = reinterpret_cast<uint16_t *>(s_wsum + 32);                               // TILE
@@ -827,21 +885,41 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 
   // ---- load keys ------------------------------------------------------------------------------------
   KeyT raw[IPT];
+  if (FULL && a.tma_keys) {
+    // the tile was fetched by the bulk copy issued at kernel entry: wait for its bytes, then read the keys from
+    // the staging buffer (consecutive lanes, consecutive keys: conflict-free).  The buffer is free again after
+    // the barrier that follows the ranking, long before the bucket-ordered keys are staged into it.
+    mbar_wait(key_bar, 0);
+    const KeyT *kt = reinterpret_cast<const KeyT *>(stage) + idx0;
 #pragma unroll
-  for (int r = 0; r < IPT; r++)
-    raw[r] = (FULL || idx0 + r * 32 < n_valid) ? *reinterpret_cast<const KeyT *>(kp + (size_t)(r * 32) * key_stride) : (KeyT)0;
+    for (int r = 0; r < IPT; r++) raw[r] = kt[r * 32];
+  } else {
+#pragma unroll
+    for (int r = 0; r < IPT; r++)
+      raw[r] = (FULL || idx0 + r * 32 < n_valid) ? *reinterpret_cast<const KeyT *>(kp + (size_t)(r * 32) * key_stride) : (KeyT)0;
+  }
   // Digits are computed once and kept packed four to a register (IPT/4 registers).
   KeyOrder ko = a.ko;
   ko.sub = LUT ? 0ull : (a.plan_in_args ? a.arg_sub : a.plan->sub);
   ko.lshift = LUT ? 0u : (a.plan_in_args ? a.arg_lshift : a.plan->lshift);
   // range reduction active (or a shift larger than this digit's offset, which the plan never produces): the
   // xor shortcut of fast_digit does not apply
-  const bool has_sub = ko.sub != 0 || (int)ko.lshift > a.shift;
+  // BYTEWISE (the host knows the plan: no range reduction, no left shift): this pass's digit and the next
+  // pass's are whole bytes of the raw key xor-ed with constants, and the code for everything else is not
+  // even compiled in (fewer registers, no spills)
+  const bool has_sub = !BYTEWISE && (ko.sub != 0 || (int)ko.lshift > a.shift);
+  const int es = a.shift - (BYTEWISE ? 0 : (int)ko.lshift);  // bit offset of this pass's digit in the (mapped, unshifted) key
+  // A slot's digit is needed once more when the staged tile is written out (which bucket a slot belongs to).  In
+  // the common case it is re-derived there from the staged key itself (one byte permute); otherwise the
+  // ranking leaves it in a byte array.
+  // (the partition pass's "digit" is a table look-up, that of range-reduced or left-shifted keys costs the full
+  //  order mapping: those are kept in a byte array by the ranking)
+  constexpr bool use_sdigit = !BYTEWISE;
   static_assert(IPT % 4 == 0, "digits are packed four per register");
   uint32_t dpack[IPT / 4];
   // 32-bit word of the raw key that holds the (byte-aligned) digit at bit offset es of the key
   auto word_at = [&](int r, int es) -> uint32_t {
-    if constexpr (KB == 8) return es >= 32 ? (uint32_t)(raw[r] >> 32) : (uint32_t)raw[r];
+    if constexpr (KB == 8) return (uint32_t)(raw[r] >> (es & 32));  // (a shift, not a select: no predicate)
     else return (uint32_t)raw[r];
   };
   auto top_word = [&](int r) -> uint32_t {  // the word whose byte TOPB carries the sign bit
@@ -853,7 +931,6 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     const DigitX dx = make_digitx(ko, a.shift);
     // padding of the last tile ranks behind everything (digit 255, last in index order)
     auto pad = [&](int r, uint32_t d) -> uint32_t { return (!FULL && idx0 + r * 32 >= n_valid) ? (uint32_t)(RADIX - 1) : d; };
-    const int es = a.shift - (int)ko.lshift;
     if constexpr (LUT) {
 #pragma unroll
       for (int q = 0; q < IPT / 4; q++) {
@@ -863,7 +940,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           w |= pad(4 * q + e, a.lut[range_bin((unsigned long long)to_ordered<KB>(raw[4 * q + e], ko), a.lut_lo, a.lut_shift, a.lut_bins)]) << (8 * e);  // partition pass
         dpack[q] = w;
       }
-    } else if (has_sub) {
+    } else if (!BYTEWISE && has_sub) {
 #pragma unroll
       for (int q = 0; q < IPT / 4; q++) {
         uint32_t w = 0;
@@ -872,7 +949,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
           w |= pad(4 * q + e, (uint32_t)(to_ordered<KB>(raw[4 * q + e], ko) >> a.shift) & (RADIX - 1)) << (8 * e);
         dpack[q] = w;
       }
-    } else if ((es & 7) == 0) {
+    } else if (BYTEWISE || (es & 7) == 0) {
       // The common case (no left shift): the digit is one byte of the raw key xor-ed with a constant, so four
       // digits are gathered into a register by three byte permutes and one xor (+ the sign handling of IEEE keys).
       const uint32_t bsel = (uint32_t)(es >> 3) & 3u;
@@ -896,7 +973,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         }
         dpack[q] = w;
       }
-    } else {
+    } else if constexpr (!BYTEWISE) {
 #pragma unroll
       for (int q = 0; q < IPT / 4; q++) {
         uint32_t w = 0;
@@ -922,8 +999,14 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     const int nshift = (int)(next_p1 - 1) * RADIX_BITS;
     const DigitX dn = make_digitx(ko, nshift);
     const bool skewed = (a.plan_in_args ? a.arg_next_skewed : a.plan->skewed[next_p1 - 1]) != 0;
-    const int esn = nshift - (int)ko.lshift;
-    if (has_sub || skewed) {
+    const int esn = nshift - (BYTEWISE ? 0 : (int)ko.lshift);
+    if (BYTEWISE && dn.nx == 0 && !skewed) {
+      // byte-aligned digit of an integer key: one byte permute (+ the constant) per key
+      const uint32_t s1 = ((uint32_t)(esn >> 3) & 3u) | 0x4440u;
+#pragma unroll
+      for (int r = 0; r < IPT; r++)
+        if (FULL || idx0 + r * 32 < n_valid) atomicAdd(&nhist[prmt(word_at(r, esn), 0u, s1) ^ dn.xc], 1u);
+    } else if (has_sub || skewed) {
 #pragma unroll
       for (int r = 0; r < IPT; r++) {
         const bool valid = FULL || idx0 + r * 32 < n_valid;
@@ -931,12 +1014,6 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         const uint32_t dnext = has_sub ? (uint32_t)(to_ordered<KB>(raw[r], ko) >> nshift) & (RADIX - 1) : fast_digit<KB>(raw[r], dn);
         if (valid) hist_add<false>(nhist, dnext, vmask);
       }
-    } else if ((esn & 7) == 0 && dn.nx == 0) {
-      // byte-aligned digit of an integer key: one byte permute (+ the constant) per key
-      const uint32_t s1 = ((uint32_t)(esn >> 3) & 3u) | 0x4440u;
-#pragma unroll
-      for (int r = 0; r < IPT; r++)
-        if (FULL || idx0 + r * 32 < n_valid) atomicAdd(&nhist[prmt(word_at(r, esn), 0u, s1) ^ dn.xc], 1u);
     } else {
 #pragma unroll
       for (int r = 0; r < IPT; r++)
@@ -947,39 +1024,26 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     // unstable: the old value of the CTA's counter is the key's rank among the tile's keys of that digit
 #pragma unroll
     for (int r = 0; r < IPT; r++) rank_set(r, atomicAdd(&wc[digit_of(r)], 1u));
-  } else if constexpr (RANK == RANK_MATCH) {
-    // Lanes holding digit d OR their lane bit into the warp's word for d; after a warp barrier the word is the
-    // peer mask.  Two generations of words alternate between rows, so that the lowest peer can clear the word
-    // it used while the next row is already filling the other generation.
-    uint32_t *wm = warp_match + warp * (2 * RADIX);
-    const uint32_t lbit = 1u << lane, lt = lanemask_lt();
-#pragma unroll
-    for (int r = 0; r < IPT; r++) {
-      const uint32_t d = digit_of(r);
-      uint32_t *m = wm + (r & 1) * RADIX + d;
-      atomicOr(m, lbit);
-      __syncwarp();
-      const uint32_t peers = *m;
-      const uint32_t cnt = wc[d];
-      __syncwarp();
-      const uint32_t lower = __popc(peers & lt);
-      rank_set(r, cnt + lower);
-      if (lower == 0) {
-        wc[d] = cnt + __popc(peers);
-        *m = 0;
-      }
-    }
   } else {
-#pragma unroll
-    for (int r = 0; r < IPT; r++) {
+    // The lowest lane of every group of equal digits adds the group's size to the warp's counter of that digit;
+    // the counter's old value is the group's first rank, handed to the other lanes by a shuffle.  (One returning
+    // shared-memory atomic by the leaders instead of a load by everyone plus a store by the leaders: the scatter
+    // pass is bound by L1TEX/shared-memory wavefronts, and rows are issued in order, so the ranks stay stable.)
+    const unsigned lt = lanemask_lt();
+    auto rank_row = [&](int r, unsigned peers) {
       const uint32_t d = digit_of(r);
-      const unsigned peers = digit_peers<false>(d);
-      const uint32_t cnt = wc[d];
-      __syncwarp();
-      const uint32_t lower = __popc(peers & lanemask_lt());
-      rank_set(r, cnt + lower);
-      if (lower == 0) wc[d] = cnt + __popc(peers);
-      __syncwarp();
+      const uint32_t lower = __popc(peers & lt);
+      uint32_t first = 0;
+      if (lower == 0) first = atomicAdd(&wc[d], (uint32_t)__popc(peers));
+      first = __shfl_sync(0xffffffffu, first, __ffs(peers) - 1);
+      rank_set(r, first + lower);
+    };
+#pragma unroll
+    for (int q = 0; q < IPT / 4; q++) {
+      rank_row(4 * q + 0, packed_digit_peers<0>(dpack[q]));
+      rank_row(4 * q + 1, packed_digit_peers<1>(dpack[q]));
+      rank_row(4 * q + 2, packed_digit_peers<2>(dpack[q]));
+      rank_row(4 * q + 3, packed_digit_peers<3>(dpack[q]));
     }
   }
   __syncthreads();
@@ -996,13 +1060,15 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       run = warp_cnt[tid];
     } else {
 #pragma unroll
-      for (int w = 0; w < NWARPS; w++) {
-        const uint32_t t = warp_cnt[w * RADIX + tid];
-        warp_cnt[w * RADIX + tid] = run;
-        run += t;
-      }
+      for (int w = 0; w < NWARPS; w++) run += warp_cnt[w * RADIX + tid];
     }
     my_count = run;
+    // the tile's count of digit tid goes out as early as possible: successors are waiting for it
+    // (counts published to other tiles exclude the padding of the last tile; tile 0 publishes its prefix below)
+    if (tile != 0) {
+      const uint64_t vc = run - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
+      st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_AGG | ((uint64_t)a.tag << LB_TAG_SHIFT) | vc);
+    }
     uint32_t inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1039,15 +1105,26 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   if (tid < RADIX) {
     uint32_t off = 0;
     for (int w = 0; w < warp; w++) off += s_wsum[w];
-    s_prefix[tid] += off;
+    const uint32_t first_slot = s_prefix[tid] + off;  // staging slot of the tile's first key of digit tid
+    s_prefix[tid] = first_slot;
+    // The counters turn into staging offsets: first slot of (this warp's) keys of the digit, so that a key's
+    // final slot is one shared-memory load away from its rank inside the warp (conflict-free here: consecutive
+    // threads, consecutive words; one random load less per key there).
+    if constexpr (RANK == RANK_ATOMIC) {
+      warp_cnt[tid] = first_slot;
+    } else {
+      uint32_t acc = first_slot;
+#pragma unroll
+      for (int w = 0; w < NWARPS; w++) {
+        const uint32_t t = warp_cnt[w * RADIX + tid];
+        warp_cnt[w * RADIX + tid] = acc;
+        acc += t;
+      }
+    }
     // counts published to other tiles exclude the padding of the last tile
     valid_count = my_count - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
     if constexpr (LUT) pdelta[tid] = a.peer_delta ? a.peer_delta[tid] : 0;
-    uint64_t *slot = &a.lookback[(size_t)tile * RADIX + tid];
-    if (tile == 0)
-      st_relaxed_u64(slot, LB_FLAG_PREFIX | tagbits | (tile0_base + valid_count));
-    else
-      st_relaxed_u64(slot, LB_FLAG_AGG | tagbits | valid_count);
+    if (tile == 0) st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (tile0_base + valid_count));
   }
   __syncthreads();  // s_prefix complete
 
@@ -1055,9 +1132,9 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
   for (int r = 0; r < IPT; r++) {
     const uint32_t d = digit_of(r);
-    const uint32_t rk = RANK == RANK_ATOMIC ? rank_get(r) + s_prefix[d] : rank_get(r) + s_prefix[d] + wc[d];
+    const uint32_t rk = rank_get(r) + wc[d];
     rank_set(r, rk);
-    sdigit[rk] = (uint8_t)d;
+    if constexpr (use_sdigit) sdigit[rk] = (uint8_t)d;
     srank[idx0 + r * 32] = (uint16_t)rk;  // payload streams pick their slot up from here
   }
 
@@ -1097,47 +1174,14 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   bool have_next = false;               // column j+1 already issued into the other buffer
   if (NSTAGE == 2) have_next = issue_next(bufs[1]);
 
-  // ---- decoupled look-back (one thread per digit), after the staging stores so that the predecessors
-  //      have had time to publish.  LB_BATCH predecessors are polled per round trip: the chain of
-  //      dependent L2 loads is what this phase costs. ------------------------------------------------------
-  if (tid < RADIX) {
-    uint64_t excl;
-    if (tile == 0) {
-      excl = tile0_base;
-    } else {
-      constexpr int LB_BATCH = 4;
-      excl = 0;
-      int64_t t = tile - 1;
-      bool done = false;
-      while (!done) {
-        uint64_t w[LB_BATCH];
-#pragma unroll
-        for (int j = 0; j < LB_BATCH; j++) {
-          const int64_t tt = t - j;
-          w[j] = tt >= 0 ? ld_relaxed_u64(&a.lookback[(size_t)tt * RADIX + tid]) : (LB_FLAG_PREFIX | tagbits);
-        }
-        int consumed = 0;
-#pragma unroll
-        for (int j = 0; j < LB_BATCH; j++) {
-          const bool ready = (w[j] & LB_TAG_MASK) == tagbits && (w[j] & LB_FLAG_MASK) != 0;
-          if (!done && consumed == j && ready) {  // consume in order, stop at the first unpublished word
-            excl += w[j] & LB_VALUE_MASK;
-            consumed = j + 1;
-            if ((w[j] & LB_FLAG_MASK) == LB_FLAG_PREFIX) done = true;
-          }
-        }
-        t -= consumed;
-        if (consumed == 0 && a.spin_ns != 0) __nanosleep(a.spin_ns);  // optional back-off while nothing is published
-      }
-      st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
-    }
-    gbase[tid] = (GOff)excl - (GOff)s_prefix[tid];  // (32-bit: wraps, the slot index added later brings it back)
-  }
-  if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
+  // FIX: the tile-local ordering only needs the staged keys, so it runs BEFORE the look-back -- the
+  // predecessors get that much more time to publish their prefixes and the look-back finds them ready.
   __shared__ uint32_t s_given_up;
-  if (FIX && tid == 0) s_given_up = ld_relaxed_u32(a.fix_flag);  // one decision for the whole tile (see below)
-  __syncthreads();  // column 0, sdigit and gbase visible to everyone
-
+  if constexpr (FIX) {
+    cp_async_wait<0>();  // column 0 has landed (mine)
+    if (tid == 0) s_given_up = ld_relaxed_u32(a.fix_flag);  // one decision for the whole tile (see below)
+    __syncthreads();     // column 0 visible to everyone
+  }
   if constexpr (FIX) {
     // Last pass of the MSB hybrid plan.  In bucket order, the tile's keys that agree on ALL swept bits
     // (>= 8*fix_cut) are adjacent: within a bucket they are still ordered by the lower swept digits.  Such a
@@ -1278,15 +1322,108 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     }
   }
 
-  GOff goff[IPT];
+  // ---- decoupled look-back (one thread per digit), after the staging stores so that the predecessors
+  //      have had time to publish.  LB_BATCH predecessors are polled per round trip: the chain of
+  //      dependent L2 loads is what this phase costs. ------------------------------------------------------
+  if (tid < RADIX) {
+    uint64_t excl;
+    if (tile == 0) {
+      excl = tile0_base;
+    } else {
+      constexpr int LB_BATCH = 4;
+      excl = 0;
+      int64_t t = tile - 1;
+      bool done = false;
+      while (!done) {
+        uint64_t w[LB_BATCH];
 #pragma unroll
-  for (int k = 0; k < IPT; k++) {
-    const int i = tid + k * THREADS;
-    goff[k] = (FULL || i < n_valid) ? (GOff)(gbase[sdigit[i]] + (GOff)(i + (FIX ? (int)sdelta[i] : 0))) : (GOff)0;
+        for (int j = 0; j < LB_BATCH; j++) {
+          const int64_t tt = t - j;
+          w[j] = tt >= 0 ? ld_relaxed_u64(&a.lookback[(size_t)tt * RADIX + tid]) : (LB_FLAG_PREFIX | tagbits);
+        }
+        int consumed = 0;
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; j++) {
+          const bool ready = (w[j] & LB_TAG_MASK) == tagbits && (w[j] & LB_FLAG_MASK) != 0;
+          if (!done && consumed == j && ready) {  // consume in order, stop at the first unpublished word
+            excl += w[j] & LB_VALUE_MASK;
+            consumed = j + 1;
+            if ((w[j] & LB_FLAG_MASK) == LB_FLAG_PREFIX) done = true;
+          }
+        }
+        t -= consumed;
+        if (consumed == 0 && a.spin_ns != 0) __nanosleep(a.spin_ns);  // optional back-off while nothing is published
+      }
+      st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (excl + valid_count));
+    }
+    gbase[tid] = (GOff)excl - (GOff)s_prefix[tid];  // (32-bit: wraps, the slot index added later brings it back)
   }
+  if constexpr (!FIX) {
+    if (NSTAGE == 2 && have_next) cp_async_wait<1>(); else cp_async_wait<0>();  // column 0 has landed (mine)
+  }
+  __syncthreads();  // column 0 and gbase visible to everyone
+
+  GOff goff[IPT];
   int wr_s = 0;  // write cursor
   uint32_t wr_c = 0;
-  for (int j = 0;; j++) {
+  int j0 = 0;    // first column the loop below writes
+  // after column j has been written out: wait for / stage the next one
+  auto next_column = [&](int j) {
+    if (NSTAGE == 2) {
+      cp_async_wait<0>();   // my part of column j+1 has landed
+      __syncthreads();      // everyone is done writing column j out, and column j+1 is complete
+      issue_next(bufs[j & 1]);  // column j+2 into the buffer column j just vacated
+    } else {
+      __syncthreads();      // everyone is done with the staging buffer
+      issue_next(bufs[0]);
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+  };
+  if constexpr (use_sdigit) {
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      const int i = tid + k * THREADS;
+      goff[k] = (FULL || i < n_valid) ? (GOff)(gbase[sdigit[i]] + (GOff)(i + (FIX ? (int)sdelta[i] : 0))) : (GOff)0;
+    }
+  } else {
+    // bucket of a slot = digit of the key staged there: byte (es/8) of the raw key, mapped like in the ranking
+    const KeyT *kcol0 = reinterpret_cast<const KeyT *>(bufs[0]);
+    const int kstep0 = soa_keys ? 1 : (int)(ks.chunk_bytes / KB);
+    const DigitX dx = make_digitx(ko, a.shift);
+    const uint32_t s1 = ((uint32_t)(es >> 3) & 3u) | 0x4440u;
+    const bool direct = soa_keys && ks.chunk_bytes == KB;  // the key array is column 0: write it out on the way
+    KeyT *kdst = reinterpret_cast<KeyT *>(ks.buf[sel ^ 1]);
+    auto slot_loop = [&](auto direct_c) {
+#pragma unroll
+      for (int k = 0; k < IPT; k++) {
+        // (groups of four: without the fence the scheduler hoists all IPT staged keys into registers at once
+        //  and spills)
+        if (k % 4 == 0 && k != 0) asm volatile("" ::: "memory");
+        const int i = tid + k * THREADS;
+        goff[k] = (GOff)0;
+        if (FULL || i < n_valid) {
+          const KeyT kv = kcol0[i * kstep0];
+          uint32_t w, top;
+          if constexpr (KB == 8) { top = (uint32_t)(kv >> 32); w = (uint32_t)(kv >> (es & 32)); }
+          else { top = (uint32_t)kv << (32 - 8 * KB); w = (uint32_t)kv; }
+          const uint32_t d = (prmt(w, 0u, s1) ^ dx.xc) ^ ((uint32_t)((int32_t)top >> 31) & dx.nx);
+          goff[k] = (GOff)(gbase[d] + (GOff)(i + (FIX ? (int)sdelta[i] : 0)));
+          if constexpr (decltype(direct_c)::value) kdst[goff[k]] = kv;
+        }
+      }
+    };
+    if (direct) {
+      slot_loop(std::true_type{});
+      wr_s = 1;
+      j0 = 1;
+      if (wr_s >= a.ss.n_streams) return;
+      next_column(0);
+    } else {
+      slot_loop(std::false_type{});
+    }
+  }
+  for (int j = j0;; j++) {
     {
       const Stream &st = a.ss.streams[wr_s];
       unsigned char *dst = st.buf[sel ^ 1];
@@ -1300,23 +1437,14 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       if (++wr_c == cpe) { wr_c = 0; wr_s++; }
     }
     if (wr_s >= a.ss.n_streams) break;
-    if (NSTAGE == 2) {
-      cp_async_wait<0>();   // my part of column j+1 has landed
-      __syncthreads();      // everyone is done writing column j out, and column j+1 is complete
-      issue_next(bufs[j & 1]);  // column j+2 into the buffer column j just vacated
-    } else {
-      __syncthreads();      // everyone is done with the staging buffer
-      issue_next(bufs[0]);
-      cp_async_wait<0>();
-      __syncthreads();
-    }
+    next_column(j);
   }
 }
 
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
 // ANYCHUNK = true additionally handles 1- and 2-byte chunks; with all five widths inlined ptxas needs
 // far more registers per thread, so the narrow widths get their own instantiation.
-template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX = false, int RANK = RANK_BALLOT, bool IDX32 = false>
+template <int KB, int THREADS, int IPT, int MINB, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX = false, int RANK = RANK_BALLOT, bool BYTEWISE = false>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is assumed");
   constexpr int TILE = THREADS * IPT;
@@ -1326,23 +1454,30 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
 
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t *warp_cnt = reinterpret_cast<uint32_t *>(smem + (size_t)NSTAGE * TILE * a.stage_bytes);
-  constexpr int RANK_WORDS = (int)(sweep_rank_smem_bytes<THREADS, RANK>() / 4);
+  constexpr int RANK_WORDS = NWARPS * RADIX;
   uint32_t *nhist = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(warp_cnt + RANK_WORDS) + RADIX * 8);  // = s_prefix
   // One tile per CTA.  (A persistent grid that loops over tickets was measured 17 % slower: CTAs that
   // start together stay in phase, so loads, look-backs and stores of the whole machine bunch up; fresh
   // CTAs per tile stagger naturally.  profiles/README.md)
   __shared__ uint32_t s_tile;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&a.tile_counter[a.pass], 1u);
-  // (RANK_ATOMIC only needs the CTA's one row of counters; the padded last tile uses the warps' rows)
+  __shared__ __align__(8) uint64_t s_key_bar;
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(&a.tile_counter[a.pass], 1u);
+    s_tile = t;
+    if (a.tma_keys && a.n - (int64_t)t * TILE >= TILE) {
+      mbar_init(&s_key_bar, 1);
+      tma_load_tile(smem, a.ss.streams[0].buf[sel] + (size_t)t * TILE * KB, (uint32_t)(TILE * KB), &s_key_bar);
+    }
+  }
   for (int i = threadIdx.x; i < RANK_WORDS / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t remaining = a.n - tile * TILE;
   if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK, IDX32, true>(a, smem, tile, TILE, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK, BYTEWISE, true>(a, smem, tile, TILE, sel, &s_key_bar);
   else
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK == RANK_ATOMIC ? RANK_BALLOT : RANK, IDX32, false>(a, smem, tile, (int)remaining, sel);
+    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK_BALLOT, BYTEWISE, false>(a, smem, tile, (int)remaining, sel, &s_key_bar);
 }
 
 // ------------------------------------------------------------------------------------------------

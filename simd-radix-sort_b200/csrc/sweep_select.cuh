@@ -1,5 +1,4 @@
-// sweep_select.cuh -- maps (key bytes, tile geometry, staging depth, chunk widths, ranking method, index
-// width) to an instantiation of onesweep_kernel.  The instantiations of each (key width, geometry) pair
+// sweep_select.cuh -- maps (key bytes, tile geometry, staging depth, chunk widths, ranking method) to an instantiation of onesweep_kernel.  The instantiations of each (key width, geometry) pair
 // live in their own translation unit (sweep_inst.cu compiled with -DSWEEP_KB=.. -DSWEEP_CFG=..) so that
 // they compile in parallel.
 #pragma once
@@ -12,7 +11,7 @@ using SweepFn = void (*)(const SweepArgs);
 struct TileCfg { int threads, ipt, minb; };
 // tile geometries of the scatter kernel (option "tile_cfg"); minb = CTAs per SM the kernel is compiled for.
 // (512x16x1 and 256x16x4 were measured slower in round 1 and are gone: profiles/README.md)
-constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}};
+constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}, {256, 16, 4}};
 constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 constexpr int kDefaultTileCfg = 0;
 
@@ -21,26 +20,33 @@ struct SweepSel {
   bool any;     // a stream with 1- or 2-byte chunks takes part
   bool lut;     // partition pass of the multi-GPU sort
   bool fix;     // last pass of the MSB hybrid plan (8-byte keys, default geometry)
-  int rank;     // RANK_BALLOT / RANK_MATCH / RANK_ATOMIC
-  bool idx32;   // n < 2^32
+  int rank;     // RANK_BALLOT / RANK_ATOMIC
+  bool bytewise;  // the host knows the plan: no range reduction, no left shift (digits are bytes of the raw key)
 };
 
-template <int KB, int THREADS, int IPT, int MINB, int RANK, bool IDX32>
+template <int KB, int THREADS, int IPT, int MINB, int RANK, bool BW>
 inline SweepFn sweep_variant2(const SweepSel &s) {
-  if constexpr (KB == 8 && THREADS == 256 && IPT == 16 && RANK != RANK_ATOMIC) {
-    if (s.fix) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, true, RANK, IDX32> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, true, RANK, IDX32>;
+  if (s.nstage == 2) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true, false, false, RANK, BW> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false, false, false, RANK, BW>;
+  return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, false, RANK, BW> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, false, RANK, BW>;
+}
+
+template <int KB, int THREADS, int IPT, int MINB, bool BW>
+inline SweepFn sweep_variant1(const SweepSel &s) {
+  if constexpr (KB == 8 && THREADS == 256 && IPT == 16) {
+    // last pass of the MSB hybrid plan (8-byte keys, default geometry): orders the final segments a tile holds
+    if (s.fix) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, true, RANK_BALLOT, BW> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, true, RANK_BALLOT, BW>;
   }
-  if (s.nstage == 2) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 2, true, false, false, RANK, IDX32> : onesweep_kernel<KB, THREADS, IPT, MINB, 2, false, false, false, RANK, IDX32>;
-  return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, false, RANK, IDX32> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, false, RANK, IDX32>;
+  // (the unstable ranking is only chosen when the host knows the plan, i.e. together with BW)
+  if constexpr (BW) {
+    if (s.rank == RANK_ATOMIC) return sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, BW>(s);
+  }
+  return sweep_variant2<KB, THREADS, IPT, MINB, RANK_BALLOT, BW>(s);
 }
 
 template <int KB, int THREADS, int IPT, int MINB>
 inline SweepFn sweep_variant(const SweepSel &s) {
-  if (s.lut) return s.rank == RANK_BALLOT ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true, false, RANK_BALLOT, false>
-                                          : onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true, false, RANK_MATCH, false>;
-  if (s.rank == RANK_ATOMIC && !s.fix) return s.idx32 ? sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, true>(s) : sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, false>(s);
-  if (s.rank == RANK_BALLOT) return s.idx32 ? sweep_variant2<KB, THREADS, IPT, MINB, RANK_BALLOT, true>(s) : sweep_variant2<KB, THREADS, IPT, MINB, RANK_BALLOT, false>(s);
-  return s.idx32 ? sweep_variant2<KB, THREADS, IPT, MINB, RANK_MATCH, true>(s) : sweep_variant2<KB, THREADS, IPT, MINB, RANK_MATCH, false>(s);
+  if (s.lut) return onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, true, false, RANK_BALLOT, false>;  // multi-GPU partition pass
+  return s.bytewise ? sweep_variant1<KB, THREADS, IPT, MINB, true>(s) : sweep_variant1<KB, THREADS, IPT, MINB, false>(s);
 }
 
 // defined in sweep_inst.cu, one translation unit per (key bytes, geometry)
