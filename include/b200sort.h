@@ -102,8 +102,9 @@ int b200sort_version(void);
 uint64_t b200sort_launch_count(void);
 
 /* Tuning/ablation knobs, process-wide.  Known names: "algo" (0 auto, 1 LSD one-sweep passes,
- * 2 hybrid MSB), "tile_cfg" (index of the scatter tile geometry), "use_match" (1 = __match_any_sync
- * ranking, 0 = ballot ranking), "hist_match", "allow_skip", "profile".  Returns 0, or B200SORT_EINVAL for an unknown name. */
+ * 2 hybrid MSB), "tile_cfg" (index of the scatter tile geometry), "first_atomic", "tma_keys", "bytewise",
+ * "hist_match", "allow_skip", "profile", "mgpu_overlap", "mgpu_chunks", "mgpu_refine" (INTEGRATION.md lists them
+ * all).  Returns 0, or B200SORT_EINVAL for an unknown name. */
 int b200sort_set_option(const char *name, int64_t value);
 int64_t b200sort_get_option(const char *name);
 
@@ -166,10 +167,39 @@ int b200sort_mgpu_plan(const uint64_t *local_hist, int bits, int world_size, con
 /* Distributed SoA sort.  On entry every rank holds `num_local` unsorted records in device memory; on
  * return rank r holds *out_num_local records, sorted, all of them ordered before those of rank r+1.
  * `capacity` is the number of records each of keys/payloads can hold (>= the largest partition; the
- * call fails with B200SORT_ENOMEM, before moving data, if a partition would not fit). */
+ * call fails with B200SORT_ENOMEM, before moving data, if a partition would not fit -- which skewed or
+ * duplicate-heavy keys do not cause: heavy key values are split, see below). */
 int b200sort_mgpu_sort_soa(b200sort_comm *comm, void *keys, int key_type, int64_t num_local,
                            int64_t capacity, int ascending, int n_payloads, void *const *payloads,
                            const uint32_t *payload_elem_bytes, int64_t *out_num_local, void *stream);
+
+/* The same for combined records (the DataElement<K, Ps...> form, radixSort.hpp:1770-1778): `records` holds
+ * `num_local` records of `record_bytes` bytes (a power of two <= 64, key of `key_type` at byte offset 0) and
+ * has room for `capacity` of them. */
+int b200sort_mgpu_sort_aos(b200sort_comm *comm, void *records, int key_type, uint32_t record_bytes,
+                           int64_t num_local, int64_t capacity, int ascending, int64_t *out_num_local,
+                           void *stream);
+
+/* 1 if the last multi-GPU sort on this communicator overlapped the exchange with the receivers' first pass
+ * (chunked partition kernels + arrival flags; uniform full-width 8-byte keys), 0 otherwise. */
+int b200sort_mgpu_used_overlap(const b200sort_comm *comm);
+
+/* Skewed keys: when a histogram bin is heavier than a rank may hold, the splitters are refined
+ * 16 key bits per level down to single key values, and the keys EQUAL to such a value are divided among the
+ * ranks by source rank and position.  The host-side logic is exported so that it can be tested without a GPU:
+ *  - b200sort_mgpu_refine_splitters: `hist_fn(ctx, n_ranges, lo, shift, nb, out)` must fill out[j * 65536 + b]
+ *    with the global count of keys u with (u - lo[j]) >> shift[j] == b < nb[j] (ordered-key space); writes the
+ *    world_size-1 splitter keys and whether each one sits on a single heavy key value;
+ *  - b200sort_mgpu_tie_thresholds: for one heavy value, `eq[s * n_blocks + b]` = number of keys equal to it in
+ *    position block b of source rank s, `less_total` = keys below it (all ranks), targets[i] = records that must
+ *    lie left of the i-th splitter sitting on it; out_blk[i] = first position block of rank `rank` whose equal
+ *    keys go right of that splitter (0: all, 0xffffffff: none). */
+typedef int (*b200sort_hist_fn)(void *ctx, int n_ranges, const uint64_t *lo, const int *shift, const uint32_t *nb,
+                                uint64_t *out);
+int b200sort_mgpu_refine_splitters(int world_size, int key_bytes, uint64_t total, b200sort_hist_fn hist_fn,
+                                   void *ctx, uint64_t *out_keys, uint32_t *out_is_tie);
+int b200sort_mgpu_tie_thresholds(int world_size, int rank, int n_blocks, uint64_t less_total, const uint32_t *eq,
+                                 int n_targets, const uint64_t *targets, uint32_t *out_blk);
 
 #ifdef __cplusplus
 }

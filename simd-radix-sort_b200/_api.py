@@ -29,6 +29,10 @@ class _Stats(ctypes.Structure):
 
 _lib = None
 
+# b200sort_hist_fn (include/b200sort.h): histogram callback of the splitter refinement
+HIST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int),
+                           ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64))
+
 
 def lib_path() -> Path:
     return _LIB_PATH
@@ -76,6 +80,16 @@ def lib():
         L.b200sort_mgpu_splitters.restype = i32
         L.b200sort_mgpu_sort_soa.argtypes = [vp, vp, i32, i64, i64, i32, i32, vpp, u32p, ctypes.POINTER(i64), vp]
         L.b200sort_mgpu_sort_soa.restype = i32
+        L.b200sort_mgpu_sort_aos.argtypes = [vp, vp, i32, u32, i64, i64, i32, ctypes.POINTER(i64), vp]
+        L.b200sort_mgpu_sort_aos.restype = i32
+        L.b200sort_mgpu_used_p2p.argtypes = [vp]
+        L.b200sort_mgpu_used_p2p.restype = i32
+        L.b200sort_mgpu_used_overlap.argtypes = [vp]
+        L.b200sort_mgpu_used_overlap.restype = i32
+        L.b200sort_mgpu_refine_splitters.argtypes = [i32, i32, ctypes.c_uint64, HIST_FN, vp, ctypes.POINTER(ctypes.c_uint64), u32p]
+        L.b200sort_mgpu_refine_splitters.restype = i32
+        L.b200sort_mgpu_tie_thresholds.argtypes = [i32, i32, i32, ctypes.c_uint64, u32p, i32, ctypes.POINTER(ctypes.c_uint64), u32p]
+        L.b200sort_mgpu_tie_thresholds.restype = i32
         _lib = L
     return _lib
 

@@ -50,6 +50,10 @@ static std::atomic<int64_t> opt_junction_table{1};  // junction kernel compares 
 static std::atomic<int64_t> opt_host_pipeline{1};  // host SoA arrays: sort keys + index while the payloads upload
 static std::atomic<int64_t> opt_mgpu_landing{1};  // multi-GPU: receive into a third set of arrays (saves the final copy)
 static std::atomic<int64_t> opt_mgpu_p2p{1};  // multi-GPU: scatter straight into peer memory (0: NCCL send/recv)
+static std::atomic<int64_t> opt_mgpu_refine{1};   // multi-GPU: refine heavy splitter bins / split heavy key values (0: fail with ENOMEM)
+static std::atomic<int64_t> opt_mgpu_overlap{1};  // multi-GPU: chunked exchange overlapped with the receivers' first pass
+static std::atomic<int64_t> opt_mgpu_chunks{4};   // ... in this many chunks
+static std::atomic<int64_t> opt_mgpu_chunk_min_log2{24};  // ... when a rank holds at least 2^this records
 static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at least 2^this records read the plan back
 
 // optional per-kernel timing (option "profile"): CUDA events around every launch of the last sort
@@ -135,7 +139,6 @@ static std::atomic<int64_t> opt_bytewise{1};      // lean kernels when the host 
 static std::atomic<int64_t> opt_first_atomic{1};  // first executed pass of a large sort: unstable atomicAdd ranking
 
 inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
-  if (cfg == 2 && kb != 8) cfg = 0;
   switch (kb * 2 + cfg) {
     case 2: return sweep_fn_inst<1, 0>(s);
     case 3: return sweep_fn_inst<1, 1>(s);
@@ -144,8 +147,7 @@ inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
     case 8: return sweep_fn_inst<4, 0>(s);
     case 9: return sweep_fn_inst<4, 1>(s);
     case 16: return sweep_fn_inst<8, 0>(s);
-    case 17: return sweep_fn_inst<8, 1>(s);
-    default: return sweep_fn_inst<8, 2>(s);  // (experimental geometry, 8-byte keys only)
+    default: return sweep_fn_inst<8, 1>(s);
   }
 }
 
@@ -162,12 +164,12 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   }
   n_cols += soa ? 1 : 0;
   const TileCfg tc = kTileCfgs[cfg];
-  const bool lut = a.lut != nullptr;
+  const bool lut = a.part.key != nullptr;
   const bool fix = !lut && a.fix_cut != 0;  // (the caller only sets fix_cut where the FIX instantiation exists)
   int rank = RANK_BALLOT;
   // digits are whole bytes of the raw key when the host knows that the plan has no range reduction and no shift
   const bool bytewise = !lut && a.plan_in_args != 0 && a.arg_sub == 0 && a.arg_lshift == 0 && opt_bytewise.load() != 0;
-  if (first_pass_unordered && bytewise && !fix && opt_first_atomic.load() != 0) rank = RANK_ATOMIC;
+  if (first_pass_unordered && a.plan_in_args != 0 && !lut && !fix && opt_first_atomic.load() != 0) rank = RANK_ATOMIC;
   // double-buffer the columns when there is more than one and minb CTAs still fit on an SM
   int nstage = (int)opt_nstage.load();
   if (nstage != 1 && nstage != 2)
@@ -316,7 +318,7 @@ struct Layout {
   size_t shadow_off[MAX_STREAMS];
   size_t land_off[MAX_STREAMS];
   size_t ctrl_off, ctrl_bytes;       // zeroed at the start of every sort
-  size_t ghist_off, ghist2_off, probe_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off, jtable_off;
+  size_t ghist_off, ghist2_off, probe_off, tilectr_off, plan_off, binbase_off, lookback_off, hyb_off, jtable_off, flags_off;
   size_t total;
   int64_t n_tiles;
 };
@@ -349,6 +351,7 @@ static void make_layout(const std::vector<StreamDesc> &streams, int64_t n, int t
   L->binbase_off = off;             off += (size_t)MAX_PASSES * RADIX * 8;
   L->jtable_off = off;              off += (size_t)L->n_tiles * RADIX * 8;   // FIX pass -> junction_fix_kernel
   off = align_up(off, 256);
+  L->flags_off = off;               off += 4096;  // multi-GPU: arrival flags written by the peers (never zeroed: epochs)
   // multi-GPU: a third copy of every stream, where the peers deliver this rank's records (see mgpu.cuh)
   for (size_t s = 0; s < streams.size(); s++) {
     L->land_off[s] = off;
@@ -374,6 +377,12 @@ struct DevSortOpts {
                                 // there (landing -> shadow -> caller -> ...), so that an even number of passes
                                 // ends in the caller's arrays without a copy
   int force_algo = 0;           // 1 / 2: use this algorithm whatever option "algo" says (the hybrid path's fall-back)
+  // Multi-GPU sort with the exchange overlapped (mgpu.cuh): the plan is fixed by the caller (hybrid: digit
+  // positions forced_cut .. 7 of the key shifted left by forced_lshift are swept, no range reduction), the
+  // control block has been cleared by the caller, and the FIRST executed pass has already been run by the
+  // caller (landing arrays -> shadow arrays, its successor's digit counted into the exact histograms).
+  bool forced = false;
+  uint32_t forced_lshift = 0, forced_cut = 0;
 };
 
 // one event per device for the plan read-back of large sorts (an event belongs to the device it was created on)
@@ -436,12 +445,13 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   uint64_t *lookback = (uint64_t *)(ws + L.lookback_off);
 
   const uint64_t launches_before = g_launches.load();
-  prof_reset();
-  CUDA_TRY(cudaMemsetAsync(ws + L.ctrl_off, 0, L.ctrl_bytes, stream));
+  if (!xo.forced) prof_reset();
+  if (!xo.forced) CUDA_TRY(cudaMemsetAsync(ws + L.ctrl_off, 0, L.ctrl_bytes, stream));
 
   const KeyOrder ko = make_key_order(key_type, ascending);
 
   int algo = xo.force_algo != 0 ? xo.force_algo : (int)opt_algo.load();
+  if (xo.forced) algo = 2;
   if (algo == 0) algo = (kb == 8 && n >= HYB_MIN_N) ? 2 : 1;
   if (algo == 2 && kb != 8) algo = 1;
 
@@ -459,7 +469,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     ProbeOut *probe = (ProbeOut *)(ws + L.probe_off);
     // large sorts (any algorithm): the host reads the plan back and launches exactly what executes, with the
     // plan's values as kernel arguments and the lean kernel instantiations they allow
-    const bool big = n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);
+    const bool big = xo.forced || n >= (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_host_plan_min_log2.load(), 0), 62);
     // Input in the landing arrays (multi-GPU): only the large hybrid flow knows on the host which pass runs
     // first; everything else simply starts with a copy into the caller's arrays.
     bool landing = xo.landing_input;
@@ -506,7 +516,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       ha.guess_p1 = opt_probe_guess.load() != 0 ? guess + 1 : 0;
       ha.ghist_exact = ghist_exact;
     }
-    CUDA_TRY(launch_hist(kb, ha, di.sm_count, /*probe=*/1, stream));
+    if (!xo.forced) CUDA_TRY(launch_hist(kb, ha, di.sm_count, /*probe=*/1, stream));
 
     ScanArgs sa{};
     sa.ghist = ghist; sa.probe = probe; sa.plan = plan; sa.n = n; sa.n_passes = kb;
@@ -527,7 +537,8 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       CUDA_TRY(cudaGetLastError());
       return 0;
     };
-    if (int rc = launch_scan()) return rc;
+    if (!xo.forced)
+      if (int rc = launch_scan()) return rc;
 
     // Large hybrid sorts read the plan back (small D2H, one host wait) and launch only what executes: the
     // exact min/max sweep and a second planning step if asked for, the histogram kernel unless the probe's
@@ -539,7 +550,29 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     HistArgs hb = ha;
     hb.ghist = ghist_exact; hb.plan = plan; hb.probe = nullptr;
     uint32_t hist_sweeps = 1;
-    if (big) {
+    if (xo.forced) {
+      // the caller's plan: sweep digit positions forced_cut .. kb-1 in LSD order; the first of them is done
+      hist_sweeps = 0;
+      uint32_t sel = 0, prev = 0;
+      bool any_prev = false;
+      for (int p = 0; p < kb; p++) {
+        hplan.skip[p] = (uint32_t)p < xo.forced_cut ? 1u : 0u;
+        hplan.src_sel[p] = sel;
+        if (!hplan.skip[p]) {
+          sel ^= 1u;
+          hplan.n_exec++;
+          if (!any_prev) hplan.first_exec_p1 = (uint32_t)p + 1; else hplan.next_exec_p1[prev] = (uint32_t)p + 1;
+          prev = (uint32_t)p;
+          any_prev = true;
+        }
+      }
+      hplan.final_sel = sel;
+      hplan.cut_digit = xo.forced_cut;
+      hplan.lshift = xo.forced_lshift;
+      hplan.hist_done = 1;
+      CUDA_TRY(cudaMemcpyAsync(plan, &hplan, sizeof hplan, cudaMemcpyHostToDevice, stream));
+      have_plan = true;
+    } else if (big) {
       plan_event = plan_event_of(dev);
       if (plan_event == nullptr) return fail(B200SORT_ECUDA, "cudaEventCreate failed on device %d", dev);
       CUDA_TRY(cudaMemcpyAsync(&hplan, plan, sizeof hplan, cudaMemcpyDeviceToHost, stream));
@@ -582,7 +615,8 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       SweepArgs wa{};
       wa.ss = (landing && first_exec) ? ss_in : ss; wa.n = n;
       const bool was_first = first_exec;
-      first_exec = false; wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
+      first_exec = false;
+      if (xo.forced && was_first) continue;  // run by the caller, overlapped with the exchange wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
       wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes; wa.spin_ns = (uint32_t)opt_spin_ns.load();
@@ -1081,6 +1115,10 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "allow_lshift")) return &opt_allow_lshift;
   if (!strcmp(name, "mgpu_p2p")) return &opt_mgpu_p2p;
   if (!strcmp(name, "mgpu_landing")) return &opt_mgpu_landing;
+  if (!strcmp(name, "mgpu_refine")) return &opt_mgpu_refine;
+  if (!strcmp(name, "mgpu_overlap")) return &opt_mgpu_overlap;
+  if (!strcmp(name, "mgpu_chunks")) return &opt_mgpu_chunks;
+  if (!strcmp(name, "mgpu_chunk_min_log2")) return &opt_mgpu_chunk_min_log2;
   if (!strcmp(name, "host_pipeline")) return &opt_host_pipeline;
   if (!strcmp(name, "junction_table")) return &opt_junction_table;
   if (!strcmp(name, "host_plan_min_log2")) return &opt_host_plan_min_log2;

@@ -62,6 +62,33 @@ __device__ __forceinline__ uint32_t range_bin(unsigned long long u, unsigned lon
   return b >= nb ? nb - 1u : (uint32_t)b;
 }
 
+// multi-GPU partition: destination rank of a record.  The W-1 splitters are pairs (key, block): the record with
+// ordered key u at local index i belongs to a rank >= r iff (u, i >> blk_shift) >= (key[r-1], blk[r-1])
+// lexicographically.  blk is 0 for an ordinary splitter (every key >= key[r-1] goes right); a splitter that
+// sits ON a heavy key value (more equal keys than a rank may hold: SURVEY 8e(3)) splits the equal keys by where
+// they lie -- by source rank and, inside the one source the boundary falls into, by position block -- which is
+// allowed because the order among equal keys is free.  The pairs are sorted, so the destination is an upper bound.
+struct PartArgs {
+  const unsigned long long *key;  // [n] splitter keys (ordered-key space), ascending; nullptr = not a partition pass
+  const uint32_t *blk;            // [n] position-block thresholds of THIS rank (0: all equal keys go right,
+                                  //     0xffffffff: none)
+  int n;                          // world - 1
+  int blk_shift;                  // block of local index i = i >> blk_shift
+  int has_tie;                    // some blk[] is nonzero (else the index is not needed)
+};
+
+__device__ __forceinline__ uint32_t part_dest(unsigned long long u, int64_t idx, const PartArgs &pa) {
+  const uint32_t b = pa.has_tie ? (uint32_t)(idx >> pa.blk_shift) : 0u;
+  int lo = 0, hi = pa.n;  // first splitter that is > (u, b)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const unsigned long long k = pa.key[mid];
+    const bool ge = u > k || (u == k && b >= pa.blk[mid]);  // (u, b) >= splitter mid
+    if (ge) lo = mid + 1; else hi = mid;
+  }
+  return (uint32_t)lo;
+}
+
 template <int KB>
 __device__ __forceinline__ typename UIntOf<KB>::type load_key(const unsigned char *base, int64_t i, uint32_t stride) {
   return *reinterpret_cast<const typename UIntOf<KB>::type *>(base + (size_t)i * stride);
@@ -664,13 +691,13 @@ struct SweepArgs {
   const Plan *plan;
   uint32_t tag;            // generation tag of this pass's status words (1..31)
   uint32_t stage_bytes;    // bytes per staged chunk (max chunk size over streams)
-  // multi-GPU partition pass: when lut != nullptr the "digit" is the destination rank looked up from the
-  // top lut_bits bits of the ordered key (lut has 2^lut_bits entries), not a radix digit
-  const uint8_t *lut;
-  int lut_shift;
-  unsigned long long lut_lo;  // bin = range_bin(ordered key, lut_lo, lut_shift, lut_bins)
-  uint32_t lut_bins;
+  // multi-GPU partition pass: when part.key != nullptr the "digit" is the destination rank of the record
+  // (part_dest), not a radix digit
+  PartArgs part;
   int lut_world;              // number of destinations (buckets in use)
+  // partition pass over a sub-range of the tiles (the chunks of the overlapped exchange): the launch covers
+  // tiles tile_first, tile_first + 1, ... (its tickets are relative to tile_first) up to record n
+  uint32_t tile_first;
   // ... and bucket d is written at byte offset peer_delta[d] from this GPU's own destination arrays: the
   // same array in the workspace of GPU d, mapped into this process (nullptr: everything stays local)
   const int64_t *peer_delta;
@@ -726,11 +753,6 @@ __device__ __forceinline__ uint32_t fast_digit(typename UIntOf<KB>::type raw, co
     const uint32_t neg = (uint32_t)((int32_t)(w << (32 - 8 * KB)) >> 31);
     return (((w >> x.bit) & (RADIX - 1)) ^ x.xc) ^ (neg & x.nx);
   }
-}
-
-template <int KB>
-__device__ __forceinline__ uint32_t lut_digit(typename UIntOf<KB>::type raw, const SweepArgs &a) {
-  return a.lut[range_bin((unsigned long long)to_ordered<KB>(raw, a.ko), a.lut_lo, a.lut_shift, a.lut_bins)];
 }
 
 // ---- staging of one chunk column of one stream ---------------------------------------------------------
@@ -937,7 +959,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
         uint32_t w = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++)
-          w |= pad(4 * q + e, a.lut[range_bin((unsigned long long)to_ordered<KB>(raw[4 * q + e], ko), a.lut_lo, a.lut_shift, a.lut_bins)]) << (8 * e);  // partition pass
+          w |= pad(4 * q + e, part_dest((unsigned long long)to_ordered<KB>(raw[4 * q + e], ko), tile_base + idx0 + (4 * q + e) * 32, a.part)) << (8 * e);  // partition pass
         dpack[q] = w;
       }
     } else if (!BYTEWISE && has_sub) {
@@ -1065,7 +1087,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     my_count = run;
     // the tile's count of digit tid goes out as early as possible: successors are waiting for it
     // (counts published to other tiles exclude the padding of the last tile; tile 0 publishes its prefix below)
-    if (tile != 0) {
+    if (tile != (int64_t)a.tile_first) {
       const uint64_t vc = run - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
       st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_AGG | ((uint64_t)a.tag << LB_TAG_SHIFT) | vc);
     }
@@ -1080,7 +1102,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   }
   // tile 0 turns the pass's exact histogram into bucket offsets (exclusive scan over the 256 counts)
   uint64_t tile0_base = 0, t0_inc = 0, t0_cnt = 0;
-  if (tile == 0 && tid < RADIX) {
+  const bool first_tile = tile == (int64_t)a.tile_first;  // the launch's first tile seeds the chain with the bucket offsets
+  if (first_tile && tid < RADIX) {
     if (a.bin_base != nullptr) {
       tile0_base = a.bin_base[tid];
     } else {
@@ -1095,7 +1118,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     }
   }
   __syncthreads();
-  if (tile == 0 && tid < RADIX && a.bin_base == nullptr) {
+  if (first_tile && tid < RADIX && a.bin_base == nullptr) {
     uint64_t off = 0;
     for (int w = 0; w < warp; w++) off += (uint64_t)gbase64[w];
     tile0_base = off + t0_inc - t0_cnt;
@@ -1124,7 +1147,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     // counts published to other tiles exclude the padding of the last tile
     valid_count = my_count - ((!FULL && tid == RADIX - 1) ? (uint32_t)(TILE - n_valid) : 0u);
     if constexpr (LUT) pdelta[tid] = a.peer_delta ? a.peer_delta[tid] : 0;
-    if (tile == 0) st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (tile0_base + valid_count));
+    if (first_tile) st_relaxed_u64(&a.lookback[(size_t)tile * RADIX + tid], LB_FLAG_PREFIX | tagbits | (tile0_base + valid_count));
   }
   __syncthreads();  // s_prefix complete
 
@@ -1327,7 +1350,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
   //      dependent L2 loads is what this phase costs. ------------------------------------------------------
   if (tid < RADIX) {
     uint64_t excl;
-    if (tile == 0) {
+    if (first_tile) {
       excl = tile0_base;
     } else {
       constexpr int LB_BATCH = 4;
@@ -1339,7 +1362,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
 #pragma unroll
         for (int j = 0; j < LB_BATCH; j++) {
           const int64_t tt = t - j;
-          w[j] = tt >= 0 ? ld_relaxed_u64(&a.lookback[(size_t)tt * RADIX + tid]) : (LB_FLAG_PREFIX | tagbits);
+          w[j] = tt >= (int64_t)a.tile_first ? ld_relaxed_u64(&a.lookback[(size_t)tt * RADIX + tid]) : (LB_FLAG_PREFIX | tagbits);
         }
         int consumed = 0;
 #pragma unroll
@@ -1462,7 +1485,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   __shared__ uint32_t s_tile;
   __shared__ __align__(8) uint64_t s_key_bar;
   if (threadIdx.x == 0) {
-    const uint32_t t = atomicAdd(&a.tile_counter[a.pass], 1u);
+    const uint32_t t = atomicAdd(&a.tile_counter[a.pass], 1u) + a.tile_first;
     s_tile = t;
     if (a.tma_keys && a.n - (int64_t)t * TILE >= TILE) {
       mbar_init(&s_key_bar, 1);

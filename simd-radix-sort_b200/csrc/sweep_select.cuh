@@ -10,8 +10,9 @@ using SweepFn = void (*)(const SweepArgs);
 
 struct TileCfg { int threads, ipt, minb; };
 // tile geometries of the scatter kernel (option "tile_cfg"); minb = CTAs per SM the kernel is compiled for.
-// (512x16x1 and 256x16x4 were measured slower in round 1 and are gone: profiles/README.md)
-constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}, {256, 16, 4}};
+// (512x16x1 was measured slower in round 1, 256x16x4 -- four CTAs per SM at 64 registers -- no faster in either
+//  round: 8.13 vs 8.18 ms per pass at 1e9 records; both are gone: profiles/README.md)
+constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}};
 constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 constexpr int kDefaultTileCfg = 0;
 
@@ -36,10 +37,7 @@ inline SweepFn sweep_variant1(const SweepSel &s) {
     // last pass of the MSB hybrid plan (8-byte keys, default geometry): orders the final segments a tile holds
     if (s.fix) return s.any ? onesweep_kernel<KB, THREADS, IPT, MINB, 1, true, false, true, RANK_BALLOT, BW> : onesweep_kernel<KB, THREADS, IPT, MINB, 1, false, false, true, RANK_BALLOT, BW>;
   }
-  // (the unstable ranking is only chosen when the host knows the plan, i.e. together with BW)
-  if constexpr (BW) {
-    if (s.rank == RANK_ATOMIC) return sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, BW>(s);
-  }
+  if (s.rank == RANK_ATOMIC) return sweep_variant2<KB, THREADS, IPT, MINB, RANK_ATOMIC, BW>(s);
   return sweep_variant2<KB, THREADS, IPT, MINB, RANK_BALLOT, BW>(s);
 }
 

@@ -89,6 +89,99 @@ def main():
     S.set_option("mgpu_p2p", 1)
     S.set_option("host_plan_min_log2", 24)
     S.set_option("algo", 0)
+
+    def check_global(tag, keys, out_k, out_src, up, cap):
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (keys, out_k, out_src))
+        if rank == 0:
+            all_in = np.concatenate([g[0] for g in gathered])
+            all_out = np.concatenate([g[1] for g in gathered])
+            src = np.concatenate([g[2] for g in gathered])
+            assert all_out.tobytes() == O.total_order_sorted_keys(all_in, up).tobytes(), f"{tag}: distributed key sequence differs"
+            src_rank, src_idx = src >> np.uint64(40), src & np.uint64((1 << 40) - 1)
+            offs = np.cumsum([0] + [len(g[0]) for g in gathered])[:-1]
+            pos = offs[src_rank.astype(np.int64)] + src_idx.astype(np.int64)
+            assert all_in[pos].tobytes() == all_out.tobytes(), f"{tag}: payload did not follow its key"
+            assert np.array_equal(np.sort(pos), np.arange(len(all_in))), f"{tag}: not a permutation"
+            assert max(len(g[1]) for g in gathered) <= cap, f"{tag}: a rank is over capacity"
+
+    # ---- skewed keys: never ENOMEM at capacity 1.125 * N / G; heavy key values are split --------
+    rngs = np.random.default_rng(1000 + rank)
+    table = np.random.default_rng(7).integers(-2**63, 2**63 - 1, size=1 << 12, dtype=np.int64)
+    n_local = 300_000
+    skew = {
+        "zero": np.zeros(n_local, np.int64),
+        "zero_one": rngs.integers(0, 2, size=n_local).astype(np.uint64),
+        "few_unique16": rngs.integers(-8, 8, size=n_local, dtype=np.int64),
+        "zipf": table[np.minimum(rngs.zipf(1.3, size=n_local), 1 << 12) - 1],
+        "gauss_f32": rngs.normal(0, 1, size=n_local).astype(np.float32),
+        "heavy_value_45pct": np.where(rngs.random(n_local) < 0.45, np.uint64(77), rngs.integers(0, 2**64, size=n_local, dtype=np.uint64)),
+        "sorted_u16": np.sort(rngs.integers(0, 2**16, size=n_local, dtype=np.uint16)),
+    }
+    cap = int(1.125 * n_local) + 64
+    for big_flow in (0, 1):
+        S.set_option("host_plan_min_log2", 0 if big_flow else 24)
+        for name, keys in skew.items():
+            for up in (True, False):
+                keys = np.ascontiguousarray(keys)
+                k = torch.zeros(cap, dtype=torch.from_numpy(keys[:1]).dtype, device=dev)
+                p = torch.zeros(cap, dtype=torch.uint64, device=dev)
+                k[:n_local].copy_(torch.from_numpy(keys))
+                p[:n_local].copy_(torch.from_numpy(np.arange(n_local, dtype=np.uint64) + (rank << 40)))
+                ptrs = (ctypes.c_void_p * 1)(p.data_ptr())
+                sizes = (ctypes.c_uint32 * 1)(8)
+                got = ctypes.c_int64(0)
+                rc = L.b200sort_mgpu_sort_soa(comm, k.data_ptr(), S.KEY_TYPES[keys.dtype.name], n_local, cap, int(up), 1, ptrs, sizes,
+                                              ctypes.byref(got), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, (name, up, L.b200sort_last_error())
+                torch.cuda.synchronize()
+                check_global(f"skew {name} up={up} big={big_flow}", keys, k[:got.value].cpu().numpy(), p[:got.value].cpu().numpy(), up, cap)
+    S.set_option("host_plan_min_log2", 24)
+
+    # ---- combined records: b200sort_mgpu_sort_aos (DataElement<int64, uint64>) ------------------------------------
+    for up in (True, False):
+        keys = O.make_keys("Gaussian", np.int64, n_local, seed=33 + rank)
+        rec = np.empty((n_local, 2), np.int64)
+        rec[:, 0] = keys
+        rec[:, 1] = (np.arange(n_local, dtype=np.uint64) + (rank << 40)).view(np.int64)
+        r = torch.zeros((cap, 2), dtype=torch.int64, device=dev)
+        r[:n_local].copy_(torch.from_numpy(rec))
+        got = ctypes.c_int64(0)
+        rc = L.b200sort_mgpu_sort_aos(comm, r.data_ptr(), S.KEY_TYPES["int64"], 16, n_local, cap, int(up), ctypes.byref(got),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, L.b200sort_last_error()
+        torch.cuda.synchronize()
+        out = r[:got.value].cpu().numpy()
+        check_global(f"aos up={up}", keys, np.ascontiguousarray(out[:, 0]), np.ascontiguousarray(out[:, 1]).view(np.uint64), up, cap)
+
+    # ---- overlapped exchange: chunked partition kernels, arrival flags, first pass of the receivers chunk by chunk ----
+    S.set_option("host_plan_min_log2", 0)      # landing arrays at test size
+    S.set_option("mgpu_chunk_min_log2", 12)
+    L.b200sort_mgpu_used_overlap.argtypes = [ctypes.c_void_p]
+    for n_chunks in (4, 3, 1):
+        S.set_option("mgpu_chunks", n_chunks)
+        for dt, up in ((np.uint64, True), (np.int64, False), (np.uint64, False)):
+            n_loc = (1 << 19) + 4099 + 77 * rank
+            keys = O.make_keys("Uniform", dt, n_loc, seed=500 + rank + n_chunks)
+            capo = int(1.125 * ((1 << 19) + 4099 + 77 * world)) + 4096
+            k = torch.zeros(capo, dtype=torch.from_numpy(keys[:1]).dtype, device=dev)
+            p = torch.zeros(capo, dtype=torch.uint64, device=dev)
+            for rep in range(2):
+                k[:n_loc].copy_(torch.from_numpy(keys))
+                p[:n_loc].copy_(torch.from_numpy(np.arange(n_loc, dtype=np.uint64) + (rank << 40)))
+                ptrs = (ctypes.c_void_p * 1)(p.data_ptr())
+                sizes = (ctypes.c_uint32 * 1)(8)
+                got = ctypes.c_int64(0)
+                rc = L.b200sort_mgpu_sort_soa(comm, k.data_ptr(), S.KEY_TYPES[np.dtype(dt).name], n_loc, capo, int(up), 1, ptrs, sizes,
+                                              ctypes.byref(got), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, L.b200sort_last_error()
+                torch.cuda.synchronize()
+            assert L.b200sort_mgpu_used_overlap(comm) == 1, "the overlapped exchange was not taken"
+            check_global(f"overlap chunks={n_chunks} {np.dtype(dt).name} up={up}", keys, k[:got.value].cpu().numpy(),
+                         p[:got.value].cpu().numpy(), up, capo)
+    S.set_option("host_plan_min_log2", 24)
+    S.set_option("mgpu_chunk_min_log2", 24)
+    S.set_option("mgpu_chunks", 4)
     dist.barrier()
     assert L.b200sort_mgpu_comm_destroy(comm) == 0
     dist.destroy_process_group()
