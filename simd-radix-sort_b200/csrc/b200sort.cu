@@ -74,10 +74,20 @@ static cudaEvent_t prof_event(int dev) {
 }
 struct ProfScope {
   bool on; ProfEntry pe; cudaStream_t st;
-  ProfScope(int kind, cudaStream_t s) : on(opt_profile.load() != 0), st(s) {
+  ProfScope(int kind, cudaStream_t s) : on(opt_profile.load() != 0), st(s), kind_(kind) {
     if (on) { pe.dev = 0; cudaGetDevice(&pe.dev); pe.kind = kind; pe.e0 = prof_event(pe.dev); pe.e1 = prof_event(pe.dev); cudaEventRecord(pe.e0, st); }
   }
-  ~ProfScope() { if (on) { cudaEventRecord(pe.e1, st); g_prof.push_back(pe); } }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(pe.e1, st); g_prof.push_back(pe); }
+    static const bool dbg = getenv("B200SORT_DEBUG_SYNC") != nullptr;  // development: wait for every kernel, say which one
+    if (dbg) {
+      static const char *names[] = {"hist", "scan", "sweep", "copyback", "segfix", "other"};
+      fprintf(stderr, "[b200sort] %s launched ...", names[kind_ < 6 ? kind_ : 5]);
+      const cudaError_t e = cudaStreamSynchronize(st);
+      fprintf(stderr, " done (%s)\n", cudaGetErrorString(e));
+    }
+  }
+  int kind_ = 5;
 };
 
 static int fail(int code, const char *fmt, ...) {
@@ -383,7 +393,11 @@ struct DevSortOpts {
   // caller (landing arrays -> shadow arrays, its successor's digit counted into the exact histograms).
   bool forced = false;
   uint32_t forced_lshift = 0, forced_cut = 0;
+  // Partial-sort mode (B200SORT_CMP_NONE with a threshold >= CMP_NONE_MIN_THRESH): the segments below the plan's
+  // cut need not be ordered as long as none has more than this many keys (0 = full sort)
+  int64_t cmp_none_thresh = 0;
 };
+constexpr int64_t CMP_NONE_MIN_THRESH = 8;  // below it nearly every sort would need the finish anyway: full sort
 
 // one event per device for the plan read-back of large sorts (an event belongs to the device it was created on)
 static cudaEvent_t plan_event_of(int dev) {
@@ -604,7 +618,9 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     // holds and repairs the tile-straddling ones with junction_fix_kernel; the full segment finish then only
     // runs if one of them reports a run that is too long.
     const bool soa = streams[0].elem_bytes == (uint32_t)kb;
-    const bool use_fix = have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == kDefaultTileCfg && opt_fix_in_pass.load() != 0;
+    // partial-sort mode: no ordering of the final segments at all, only a check that none exceeds the threshold
+    const bool partial = have_plan && hplan.cut_digit != 0 && xo.cmp_none_thresh >= CMP_NONE_MIN_THRESH;
+    const bool use_fix = !partial && have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == kDefaultTileCfg && opt_fix_in_pass.load() != 0;
     int last_pass = -1;
     bool first_exec = true;
     if (landing && hplan.n_exec == 0) {  // nothing will move the records: deliver them
@@ -616,7 +632,8 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       wa.ss = (landing && first_exec) ? ss_in : ss; wa.n = n;
       const bool was_first = first_exec;
       first_exec = false;
-      if (xo.forced && was_first) continue;  // run by the caller, overlapped with the exchange wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
+      if (xo.forced && was_first) continue;  // run by the caller, overlapped with the exchange
+      wa.ko = ko; wa.pass = p; wa.shift = p * RADIX_BITS;
       wa.bin_base = nullptr; wa.ghist = ghist_exact;
       wa.lookback = lookback; wa.tile_counter = tile_counter; wa.plan = plan;
       wa.tag = (uint32_t)(p + 1); wa.stage_bytes = stage_bytes; wa.spin_ns = (uint32_t)opt_spin_ns.load();
@@ -674,6 +691,20 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
       // segment finish repairs everything (and delivers the result into the caller's arrays), else the result
       // is copied out of the shadow if it ended there.  No host round trip in between.
       if (int rc = launch_segfix(&ctrl->flags[1])) return rc;
+      if (hplan.final_sel == 1)
+        if (int rc = launch_copyback(true, &ctrl->flags[1])) return rc;
+      fix_flow = true;
+    } else if (partial) {
+      PartialCheckArgs pa{};
+      pa.ss = ss; pa.n = n; pa.ko = ko; pa.ko.sub = hplan.sub; pa.ko.lshift = hplan.lshift; pa.cut = hplan.cut_digit; pa.sel = hplan.final_sel;
+      pa.thresh = xo.cmp_none_thresh; pa.flag = &ctrl->flags[1];
+      {
+        ProfScope ps(PK_SEGFIX, stream);
+        partial_check_kernel<8><<<di.sm_count * 8, 256, 0, stream>>>(pa);
+      }
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      if (int rc = launch_segfix(&ctrl->flags[1])) return rc;  // runs only if a segment longer than the threshold is out of order
       if (hplan.final_sel == 1)
         if (int rc = launch_copyback(true, &ctrl->flags[1])) return rc;
       fix_flow = true;
@@ -931,7 +962,7 @@ static int sort_host_pipelined(int key_type, bool ascending, int64_t n, const st
 }
 
 static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<StreamDesc> &streams, void *stream_v,
-                    void *workspace, size_t workspace_bytes) {
+                    void *workspace, size_t workspace_bytes, const DevSortOpts &base = DevSortOpts()) {
   cudaStream_t stream = (cudaStream_t)stream_v;
   if (n <= 1) return B200SORT_OK;  // src/radix_sort.hpp:276: nothing to do for 0 or 1 element
   int ndev = 0;
@@ -954,11 +985,11 @@ static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<S
   if (side0 == SIDE_DEVICE) {
     DeviceScope scope;  // sort on the device that owns the arrays (include/b200sort.h)
     if (scope.enter(dev0) != 0) return fail(B200SORT_ECUDA, "cannot make device %d current", dev0);
-    return sort_device(key_type, ascending, n, streams, stream, workspace, workspace_bytes);
+    return sort_device(key_type, ascending, n, streams, stream, workspace, workspace_bytes, base);
   }
 
   // ---- host arrays, SoA with payloads, big enough to care: pipelined staging --------------------------
-  if (opt_host_pipeline.load() != 0 && workspace == nullptr && streams.size() >= 2 &&
+  if (opt_host_pipeline.load() != 0 && base.cmp_none_thresh == 0 && workspace == nullptr && streams.size() >= 2 &&
       streams[0].elem_bytes == (uint32_t)key_bytes_of(key_type) && n >= ((int64_t)1 << 20) && n < ((int64_t)1 << 32)) {
     size_t need = 0;
     for (size_t s = 0; s < streams.size(); s++) need += (size_t)n * streams[s].elem_bytes * (s ? 2 : 1);
@@ -995,7 +1026,7 @@ static int sort_any(int key_type, bool ascending, int64_t n, const std::vector<S
     e = cudaMemcpyAsync(dstreams[s].ptr, streams[s].ptr, (size_t)n * streams[s].elem_bytes, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) rc = fail(B200SORT_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
   }
-  if (rc == 0) rc = sort_device(key_type, ascending, n, dstreams, stream, workspace, workspace_bytes);
+  if (rc == 0) rc = sort_device(key_type, ascending, n, dstreams, stream, workspace, workspace_bytes, base);
   for (size_t s = 0; s < streams.size() && rc == 0; s++) {
     e = cudaMemcpyAsync(streams[s].ptr, dstreams[s].ptr, (size_t)n * streams[s].elem_bytes, cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) rc = fail(B200SORT_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e));
@@ -1046,10 +1077,13 @@ int b200sort_sort_soa_ex(void *keys, int key_type, int64_t num, int ascending, i
                          void *workspace, size_t workspace_bytes) {
   if (cmp_sorter != B200SORT_CMP_INSERTION && cmp_sorter != B200SORT_CMP_NONE)
     return fail(B200SORT_EINVAL, "unknown cmp_sorter %d", cmp_sorter);
-  (void)cmp_sort_threshold;  // a full sort satisfies the partial-sort contract of every threshold
+  // CmpSorterInsertionSort: the full sort whatever the threshold.  CmpSorterNoSort: buckets of at most
+  // cmp_sort_threshold elements may stay unordered (src/radix_sort.hpp:279, src/cmp_sorters.hpp:66-78).
+  DevSortOpts base;
+  if (cmp_sorter == B200SORT_CMP_NONE && cmp_sort_threshold >= CMP_NONE_MIN_THRESH) base.cmp_none_thresh = cmp_sort_threshold;
   std::vector<StreamDesc> streams;
   if (int rc = check_soa(keys, key_type, num, n_payloads, payloads, payload_elem_bytes, &streams)) return rc;
-  return sort_any(key_type, ascending != 0, num, streams, stream, workspace, workspace_bytes);
+  return sort_any(key_type, ascending != 0, num, streams, stream, workspace, workspace_bytes, base);
 }
 
 int b200sort_sort_aos_ex(void *records, int key_type, uint32_t record_bytes, int64_t num, int ascending,
@@ -1057,10 +1091,11 @@ int b200sort_sort_aos_ex(void *records, int key_type, uint32_t record_bytes, int
                          size_t workspace_bytes) {
   if (cmp_sorter != B200SORT_CMP_INSERTION && cmp_sorter != B200SORT_CMP_NONE)
     return fail(B200SORT_EINVAL, "unknown cmp_sorter %d", cmp_sorter);
-  (void)cmp_sort_threshold;
+  DevSortOpts base;
+  if (cmp_sorter == B200SORT_CMP_NONE && cmp_sort_threshold >= CMP_NONE_MIN_THRESH) base.cmp_none_thresh = cmp_sort_threshold;
   std::vector<StreamDesc> streams;
   if (int rc = check_aos(records, key_type, record_bytes, num, &streams)) return rc;
-  return sort_any(key_type, ascending != 0, num, streams, stream, workspace, workspace_bytes);
+  return sort_any(key_type, ascending != 0, num, streams, stream, workspace, workspace_bytes, base);
 }
 
 int b200sort_sort_soa(void *keys, int key_type, int64_t num, int ascending, int n_payloads, void *const *payloads,

@@ -210,6 +210,42 @@ __global__ void __launch_bounds__(SF_THREADS, 4) segfix_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Partial-sort mode (CmpSorterNoSort, src/cmp_sorters.hpp:66-78 with the threshold of src/radix_sort.hpp:279):
+// the reference stops its recursion at buckets of at most `thresh` elements and leaves them as they are.  Here
+// the digit sweeps stop at the plan's cut; this key-only sweep then checks the contract instead of finishing
+// the segments: a segment (run of keys that agree on all swept bits) may stay unordered if it has at most
+// `thresh` keys.  Only a segment that is LONGER than the threshold and actually out of order raises the flag
+// that makes the (gated) full segment finish run.  One coalesced read of the keys; no record moves.
+// ------------------------------------------------------------------------------------------------
+struct PartialCheckArgs {
+  StreamSet ss;
+  int64_t n;
+  KeyOrder ko;   // with the plan's range reduction / shift applied by the host
+  uint32_t cut, sel;
+  int64_t thresh;
+  uint32_t *flag;
+};
+
+template <int KB>
+__global__ void __launch_bounds__(256) partial_check_kernel(const __grid_constant__ PartialCheckArgs a) {
+  using O = typename OrdOf<KB>::type;
+  const Stream &ks = a.ss.streams[0];
+  const uint32_t key_stride = ks.chunk_bytes * ks.chunks_per_elem;
+  const unsigned char *kbuf = ks.buf[a.sel];
+  const O pmask = (O)(~(O)0) << (8 * a.cut);
+  auto okey = [&](int64_t i) -> O { return to_ordered<KB>(load_key<KB>(kbuf, i, key_stride), a.ko); };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const O k1 = okey(i), k0 = okey(i - 1);
+    if (((k0 ^ k1) & pmask) != 0 || k1 >= k0) continue;  // segment boundary, or the pair is in order
+    // an out-of-order pair inside a segment: fine if the segment has at most `thresh` keys
+    int64_t len = 2;
+    for (int64_t j = i - 2; j >= 0 && len <= a.thresh && ((okey(j) ^ k1) & pmask) == 0; j--) len++;
+    for (int64_t j = i + 1; j < a.n && len <= a.thresh && ((okey(j) ^ k1) & pmask) == 0; j++) len++;
+    if (len > a.thresh) atomicOr(a.flag, 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Junction fix: companion of the FIX instantiation of onesweep_kernel.  The last pass has put every
 // final segment in order as far as one tile held it; what can still be out of order are segments whose
 // keys came from two (or more) consecutive tiles.  In the output such a segment lies across a "junction":

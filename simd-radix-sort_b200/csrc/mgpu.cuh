@@ -551,6 +551,12 @@ struct MgpuTrace {
     mark("start");
   }
   void mark(const char *name) {
+    static const bool dbg = getenv("B200SORT_MGPU_DEBUG") != nullptr;  // host-side progress lines (locating a hang)
+    if (dbg) {
+      fprintf(stderr, "[b200sort mgpu] reached %s ...", name);
+      const cudaError_t e = cudaStreamSynchronize(st);
+      fprintf(stderr, " device done (%s)\n", cudaGetErrorString(e));
+    }
     if (!on) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -962,7 +968,7 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
   // still on the NVLink.
   const int64_t chunk_min = (int64_t)1 << std::min<int64_t>(std::max<int64_t>(opt_mgpu_chunk_min_log2.load(), 12), 40);
   int n_chunks = (int)std::min<int64_t>(std::max<int64_t>(opt_mgpu_chunks.load(), 1), MGPU_MAX_CHUNKS);
-  bool overlap = landing && !heavy && kb == 8 && world <= 8 && world >= 2 && lo == 0 && shift == 8 * kb - bits &&
+  bool overlap = landing && !heavy && kb == 8 && world <= 8 && (world >= 2 || opt_mgpu_overlap.load() == 2) && lo == 0 && shift == 8 * kb - bits &&
                  opt_mgpu_overlap.load() != 0 && opt_mgpu_p2p.load() != 0 && !c->p2p_failed && cfg == kDefaultTileCfg &&
                  streams[0].elem_bytes == (uint32_t)kb;
   uint32_t d_lshift[8] = {0}, d_cut[8] = {0};

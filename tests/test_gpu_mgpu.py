@@ -18,7 +18,15 @@ def test_two_rank_distributed_sort():
     port = str(29600 + os.getpid() % 1000)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", port, str(ROOT / "tests" / "mgpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     for rank in range(world):
         assert f"MGPU_GPU_OK {rank}" in r.stdout
+
+
+def test_one_rank_communicator_runs_every_multi_gpu_code_path():
+    """a world of one on one GPU (NCCL allows it): splitters, counting, the peer-store partition kernel into this
+    rank's own landing arrays, the chunked / overlapped exchange with its arrival flags, the forced-plan local sort,
+    heavy key values -- everything except real peer traffic.  Runs on the driver's single-GPU box."""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "mgpu_single.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "MGPU_SINGLE_OK" in r.stdout, (r.stdout + r.stderr)[-3000:]

@@ -513,3 +513,70 @@ def test_host_arrays_pipelined_staging(pinned):
         assert np.array_equal(np.sort(src), np.arange(n)) and keys[src].tobytes() == k.tobytes()
         assert np.array_equal(ps[1], (src % 65521).astype(np.uint16))
         assert np.array_equal(ps[2], pays[2][src])
+
+
+# ------------------------------------------------------------------------------------------------
+# the advanced overload sort<Up, BitSorter, CmpSorterNoSort>(thresh, ...) -- buckets of at most
+# `thresh` elements stay unordered (src/radix_sort.hpp:279, src/cmp_sorters.hpp:66-78).  On the GPU: the digit
+# sweeps run, the segment finish does not (a key-only check replaces it).
+# ------------------------------------------------------------------------------------------------
+def _within_thresh_of_sorted(out_o, sorted_o, thresh):
+    """every element is less than `thresh` places away from a position where the full sort could have put it"""
+    n = len(out_o)
+    lo = sorted_o[np.maximum(np.arange(n) - (thresh - 1), 0)]
+    hi = sorted_o[np.minimum(np.arange(n) + (thresh - 1), n - 1)]
+    return bool(np.all((out_o >= lo) & (out_o <= hi)))
+
+
+@pytest.mark.parametrize("thresh", [16, 64, 4])
+def test_cmp_sorter_none_partial_sort_contract(thresh):
+    n = (1 << 20) + 333
+    rng = np.random.default_rng(thresh)
+    CMP_NONE = 1
+    try:
+        S.set_option("host_plan_min_log2", 0)
+        S.set_option("margin_bits", -2)   # about four keys per final segment: plenty of unordered small buckets
+        for dt, up in ((np.uint64, True), (np.int64, False), (np.float64, True)):
+            keys = O.make_keys("Uniform", dt, n, seed=9 + thresh)
+            idx = np.arange(n, dtype=np.uint32)
+            k, p = dev(keys), dev(idx)
+            before = S.launch_count()
+            S.sort(n, k, p, up=up, cmp_sort_threshold=thresh, cmp_sorter=CMP_NONE)
+            torch.cuda.synchronize()
+            st = S.last_stats()
+            hk, hp = host(k), host(p)
+            assert np.array_equal(np.sort(hp), idx) and keys[hp].tobytes() == hk.tobytes()      # a permutation, payloads follow
+            so = O.order_key(O.total_order_sorted_keys(keys, up), up)
+            assert _within_thresh_of_sorted(O.order_key(hk, up), so, max(thresh, 1)), (dt, up, thresh)
+            if thresh >= 8:
+                # the early-out really happened: no segment finish, and the result is NOT the full sort
+                assert st["algo"] == 2 and st["segfix_passes"] == 0 and st["cut_digit"] >= 2, st
+                assert hk.tobytes() != O.total_order_sorted_keys(keys, up).tobytes()
+            else:
+                assert hk.tobytes() == O.total_order_sorted_keys(keys, up).tobytes()              # small thresholds: full sort
+        # a segment longer than the threshold (1000 distinct keys sharing all swept bits) must still be sorted
+        g = np.arange(n) // 1000
+        f = rng.integers(0, 2**32, size=g.max() + 1, dtype=np.uint64)
+        keys = (f[g] << np.uint64(32)) | rng.integers(0, 2**32, size=n, dtype=np.uint64)
+        k = dev(keys)
+        S.sort(n, k, up=True, cmp_sort_threshold=max(thresh, 8), cmp_sorter=CMP_NONE)
+        torch.cuda.synchronize()
+        hk = host(k)
+        so = np.sort(keys)
+        assert np.array_equal(np.sort(hk), so) and _within_thresh_of_sorted(hk, so, max(thresh, 8))
+        # AoS entry point
+        rec = O.make_records(O.make_keys("Uniform", np.int64, n, seed=3), 16)
+        r = dev(rec)
+        L = S.lib()
+        import ctypes
+        rc = L.b200sort_sort_aos_ex(ctypes.c_void_p(r.data_ptr()), S.KEY_TYPES["int64"], 16, n, 1, 32, CMP_NONE,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), None, 0)
+        assert rc == 0, L.b200sort_last_error()
+        torch.cuda.synchronize()
+        out = host(r)
+        ok = np.ascontiguousarray(out[:, :8]).reshape(-1).view(np.int64)
+        assert _within_thresh_of_sorted(O.order_key(ok, True), O.order_key(np.sort(ok), True), 32)
+        assert out.tobytes() == O.make_records(ok, 16).tobytes()   # records stayed whole
+    finally:
+        S.set_option("host_plan_min_log2", 24)
+        S.set_option("margin_bits", 2)

@@ -9,6 +9,7 @@
 #   sb:ARGS                  simd-radix-sort_b200/sortbench ARGS
 #   cub[:N]                  tools/cub_compare N   (comparison row only)
 #   pytest:ARGS              python -m pytest ARGS -x -q
+#   py:SECONDS:ARGS          timeout SECONDS python ARGS   (B200SORT_MGPU_DEBUG=1)
 #   mbench:N[:ARGS]          torchrun --nproc-per-node N bench.py --gpus N ARGS  (with B200SORT_MGPU_TRACE=1)
 #   launches:ARGS            ncu launch list of bench.py ARGS -> gpurun_out/<name>_launches.csv
 #   ncu:KERNEL:SKIP:ARGS     ncu --set full of launch #SKIP of KERNEL in sortbench ARGS -> gpurun_out/<name>_KERNEL.ncu-rep
@@ -27,10 +28,12 @@ for st in "$@"; do
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> "$log" 2>&1 ;;
     bench) timeout 900 python bench.py $rest >> "$log" 2>&1 ;;
     sb) timeout 600 $SB $rest >> "$log" 2>&1 ;;
+    sbq) timeout 25 $SB $rest >> "$log" 2>&1 ;;
     cub) timeout 600 tools/cub_compare $rest >> "$log" 2>&1 ;;
     pytest) timeout 1500 python -m pytest $rest -x -q >> "$log" 2>&1 ;;
+    py) t=${rest%%:*}; args=${rest#*:}; timeout $t python $args >> "$log" 2>&1 ;;
     mbench) n=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
-            B200SORT_MGPU_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n $args >> "$log" 2>&1 ;;
+            B200SORT_MGPU_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n $args >> "$log" 2>&1 ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${name}_launches.csv python bench.py $rest >> "$log" 2>&1 ;;
     ncu) k=${rest%%:*}; r2=${rest#*:}; skip=${r2%%:*}; args=${r2#*:}
          timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/${name}_$k $SB $args >> "$log" 2>&1 ;;
