@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--records", dest="n", type=int, default=0, help="records per GPU (development override)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=0, help="records of the CPU baseline sample (default: per config)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (development / ablations)")
     return ap.parse_args()
 
 
@@ -348,6 +349,9 @@ def main():
         if rc:
             raise S.B200SortError(rc, S.lib().b200sort_last_error().decode())
 
+    for o in args.opt:
+        name, val = o.split("=")
+        S.set_option(name, int(val))
     cfg = "c2" if multi else args.config
     C = CONFIGS[cfg]
     n = args.n or C["n"]

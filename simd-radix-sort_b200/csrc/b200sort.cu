@@ -53,6 +53,8 @@ static std::atomic<int64_t> opt_mgpu_p2p{1};  // multi-GPU: scatter straight int
 static std::atomic<int64_t> opt_mgpu_refine{1};   // multi-GPU: refine heavy splitter bins / split heavy key values (0: fail with ENOMEM)
 static std::atomic<int64_t> opt_mgpu_overlap{1};  // multi-GPU: chunked exchange overlapped with the receivers' first pass
 static std::atomic<int64_t> opt_mgpu_chunks{4};   // ... in this many chunks
+static std::atomic<int64_t> opt_mgpu_wide{1};     // multi-GPU: 16-byte peer stores of element pairs
+static std::atomic<int64_t> opt_mgpu_cons_smem_kb{80};  // overlapped first pass: shared memory requested per CTA (80 KB: at most two per SM)
 static std::atomic<int64_t> opt_mgpu_chunk_min_log2{24};  // ... when a rank holds at least 2^this records
 static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at least 2^this records read the plan back
 
@@ -163,8 +165,10 @@ inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
 
 // first_pass_unordered: the caller knows that this launch is the first executed pass of the sort and that its
 // digit's histogram is not skewed -- the unstable ranking may be used
+// smem_floor: request at least this much dynamic shared memory (bounds how many CTAs of this launch an SM holds:
+// the overlapped first pass of the multi-GPU sort must leave room for the partition kernel's CTAs)
 static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int sm_count, cudaStream_t st,
-                                bool first_pass_unordered = false) {
+                                bool first_pass_unordered = false, size_t smem_floor = 0) {
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   int n_cols = 0;
   const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == (uint32_t)kb;
@@ -192,8 +196,12 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   a2.tma_keys = (opt_tma_keys.load() != 0 && soa && (((uintptr_t)a.ss.streams[0].buf[0] | (uintptr_t)a.ss.streams[0].buf[1]) & 15) == 0 &&
                  ((size_t)tc.threads * tc.ipt * kb) % 16 == 0) ? 1u : 0u;
   SweepFn k = sweep_fn(kb, cfg, sel);
-  const size_t smem = sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut);
+  const size_t smem = std::min(std::max(sweep_smem_bytes(tc, a.stage_bytes, nstage, fix, lut), smem_floor), smem_optin);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // one shared-memory carve-out for every instantiation: kernels that want different L1 / shared-memory splits
+  // cannot be resident on an SM together (the overlapped exchange runs two of them side by side)
+  e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
   (void)sm_count;
@@ -1153,6 +1161,8 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "mgpu_refine")) return &opt_mgpu_refine;
   if (!strcmp(name, "mgpu_overlap")) return &opt_mgpu_overlap;
   if (!strcmp(name, "mgpu_chunks")) return &opt_mgpu_chunks;
+  if (!strcmp(name, "mgpu_wide")) return &opt_mgpu_wide;
+  if (!strcmp(name, "mgpu_cons_smem_kb")) return &opt_mgpu_cons_smem_kb;
   if (!strcmp(name, "mgpu_chunk_min_log2")) return &opt_mgpu_chunk_min_log2;
   if (!strcmp(name, "host_pipeline")) return &opt_host_pipeline;
   if (!strcmp(name, "junction_table")) return &opt_junction_table;

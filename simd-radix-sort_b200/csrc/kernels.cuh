@@ -75,9 +75,20 @@ struct PartArgs {
   int n;                          // world - 1
   int blk_shift;                  // block of local index i = i >> blk_shift
   int has_tie;                    // some blk[] is nonzero (else the index is not needed)
+  // fast form (one box, 8-byte keys, no ties, splitters with zero low words = bin boundaries of full-width keys):
+  // destination = number of r < 7 with (high word of u) > hi_m1[r]   (0xffffffff: never)
+  uint32_t hi_only;
+  uint32_t hi_m1[7];
 };
 
 __device__ __forceinline__ uint32_t part_dest(unsigned long long u, int64_t idx, const PartArgs &pa) {
+  if (pa.hi_only) {
+    const uint32_t h = (uint32_t)(u >> 32);
+    uint32_t d = 0;
+#pragma unroll
+    for (int r = 0; r < 7; r++) d += h > pa.hi_m1[r] ? 1u : 0u;
+    return d;
+  }
   const uint32_t b = pa.has_tie ? (uint32_t)(idx >> pa.blk_shift) : 0u;
   int lo = 0, hi = pa.n;  // first splitter that is > (u, b)
   while (lo < hi) {
@@ -211,6 +222,15 @@ __device__ __forceinline__ void peer_step(unsigned &peers, uint32_t word) {
       "}"
       : "+r"(peers)
       : "r"(word), "n"(MASK));
+}
+// (partition pass of the multi-GPU sort on one box: at most 8 destinations, three bits tell them apart)
+template <int BYTE>
+__device__ __forceinline__ unsigned packed_digit_peers3(uint32_t word) {
+  unsigned peers = 0xffffffffu;
+  peer_step<1u << (8 * BYTE + 0)>(peers, word);
+  peer_step<1u << (8 * BYTE + 1)>(peers, word);
+  peer_step<1u << (8 * BYTE + 2)>(peers, word);
+  return peers;
 }
 template <int BYTE>
 __device__ __forceinline__ unsigned packed_digit_peers(uint32_t word) {
@@ -698,6 +718,7 @@ struct SweepArgs {
   // partition pass over a sub-range of the tiles (the chunks of the overlapped exchange): the launch covers
   // tiles tile_first, tile_first + 1, ... (its tickets are relative to tile_first) up to record n
   uint32_t tile_first;
+  uint32_t peer_wide;         // partition pass: 16-byte stores of element pairs into the destination arrays
   // ... and bucket d is written at byte offset peer_delta[d] from this GPU's own destination arrays: the
   // same array in the workspace of GPU d, mapped into this process (nullptr: everything stays local)
   const int64_t *peer_delta;
@@ -833,7 +854,7 @@ __device__ __forceinline__ void stage_sync(const unsigned char *src, unsigned ch
 template <typename T, int THREADS, int IPT, bool FULL, bool PEER = false, typename GOff = int64_t>
 __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned char *buf, const GOff (&goff)[IPT], int n_valid,
                                           uint32_t cpe, uint32_t c, const int64_t *pdelta = nullptr, const uint32_t *s_prefix = nullptr,
-                                          const int64_t *gbase = nullptr, int n_buckets = 0) {
+                                          const int64_t *gbase = nullptr, int n_buckets = 0, bool wide = false) {
   const T *stage = reinterpret_cast<const T *>(buf) + threadIdx.x;
   T *d = reinterpret_cast<T *>(dst) + c;
   if constexpr (PEER) {
@@ -849,6 +870,27 @@ __device__ __forceinline__ void write_out(unsigned char *dst, const unsigned cha
       const int64_t g0 = gbase[b] + s0;  // destination index of the bucket's first staged slot
       T *dp = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(d) + pdelta[b]);
       const T *sp = reinterpret_cast<const T *>(buf);
+      if (sizeof(T) == 8 && cpe == 1 && wide && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+        // 8-byte elements: every lane moves the PAIR of elements that forms one aligned 16-byte word of the
+        // destination, a warp 512 contiguous bytes of it (half the store instructions, twice the bytes per
+        // NVLink write; the two staged elements are loaded separately: their shared-memory address need not be
+        // 16-byte aligned).  Only the first / last element of a run can be a single.
+        for (int64_t pp = (((g0 >> 1) & ~(int64_t)31) + threadIdx.x); pp * 2 < g0 + cnt; pp += THREADS) {
+          const int ea = (int)(pp * 2 - g0), eb = ea + 1;
+          const bool va = ea >= 0, vb = eb >= 0 && eb < cnt;  // (ea < cnt by the loop bound)
+          if (va && vb) {
+            ulonglong2 v;
+            memcpy(&v.x, &sp[s0 + ea], 8);
+            memcpy(&v.y, &sp[s0 + eb], 8);
+            *reinterpret_cast<ulonglong2 *>(dp + pp * 2) = v;
+          } else if (va) {
+            dp[pp * 2] = sp[s0 + ea];
+          } else if (vb) {
+            dp[pp * 2 + 1] = sp[s0 + eb];
+          }
+        }
+        continue;
+      }
       for (int e = (int)threadIdx.x - (int)(g0 & 31); e < cnt; e += THREADS)
         if (e >= 0) dp[(size_t)(g0 + e) * cpe] = sp[s0 + e];
     }
@@ -1060,12 +1102,23 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       first = __shfl_sync(0xffffffffu, first, __ffs(peers) - 1);
       rank_set(r, first + lower);
     };
+    // (LUT, full tile, at most 8 destinations: the digits are < 8; a padded last tile has digit 255 in it)
+    if (LUT && FULL && a.lut_world <= 8) {
 #pragma unroll
-    for (int q = 0; q < IPT / 4; q++) {
-      rank_row(4 * q + 0, packed_digit_peers<0>(dpack[q]));
-      rank_row(4 * q + 1, packed_digit_peers<1>(dpack[q]));
-      rank_row(4 * q + 2, packed_digit_peers<2>(dpack[q]));
-      rank_row(4 * q + 3, packed_digit_peers<3>(dpack[q]));
+      for (int q = 0; q < IPT / 4; q++) {
+        rank_row(4 * q + 0, packed_digit_peers3<0>(dpack[q]));
+        rank_row(4 * q + 1, packed_digit_peers3<1>(dpack[q]));
+        rank_row(4 * q + 2, packed_digit_peers3<2>(dpack[q]));
+        rank_row(4 * q + 3, packed_digit_peers3<3>(dpack[q]));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < IPT / 4; q++) {
+        rank_row(4 * q + 0, packed_digit_peers<0>(dpack[q]));
+        rank_row(4 * q + 1, packed_digit_peers<1>(dpack[q]));
+        rank_row(4 * q + 2, packed_digit_peers<2>(dpack[q]));
+        rank_row(4 * q + 3, packed_digit_peers<3>(dpack[q]));
+      }
     }
   }
   __syncthreads();
@@ -1452,11 +1505,11 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
       unsigned char *dst = st.buf[sel ^ 1];
       const unsigned char *buf = bufs[NSTAGE == 2 ? (j & 1) : 0];
       const uint32_t cb = st.chunk_bytes, cpe = st.chunks_per_elem;
-      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
-      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
-      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
-      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
-      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world);
+      if (cb == 8) write_out<uint64_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world, a.peer_wide != 0);
+      else if (cb == 4) write_out<uint32_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world, a.peer_wide != 0);
+      else if (cb == 16) write_out<uint4, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world, a.peer_wide != 0);
+      else if (cb == 2) write_out<uint16_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world, a.peer_wide != 0);
+      else write_out<uint8_t, THREADS, IPT, FULL, LUT>(dst, buf, goff, n_valid, cpe, wr_c, pdelta, s_prefix, gbase64, a.lut_world, a.peer_wide != 0);
       if (++wr_c == cpe) { wr_c = 0; wr_s++; }
     }
     if (wr_s >= a.ss.n_streams) break;

@@ -244,6 +244,10 @@ struct DestCountArgs {
   uint32_t *digit_hist;        // [world][RADIX] or nullptr
   uint32_t digit_lshift[8];    // per destination: digit = ((u << lshift) >> shift) & 255
   uint32_t digit_shift[8];
+  // fast form of the destination (8-byte keys, no ties, splitters with zero low words -- bin boundaries of
+  // full-width keys): destination = number of r with (high word of u) > hi_m1[r]
+  uint32_t hi_only;
+  uint32_t hi_m1[8];           // 0xffffffff: never
 };
 
 template <int KB, int NLD>
@@ -258,10 +262,38 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
   __syncthreads();
   const bool dense = a.stride == KB && (((uintptr_t)a.keys) & 15) == 0;
   uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // world <= 8: lane-private counters
+  uint32_t n_ge[7] = {0, 0, 0, 0, 0, 0, 0}, n_all = 0;
   for (int64_t tile = a.tile_lo + blockIdx.x; tile < a.tile_hi; tile += gridDim.x) {
     KT kt;
     kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);
     const int64_t base = tile * KT::TILE;
+    const bool full = kt.valid == (KT::PER_THREAD >= 32 ? 0xffffffffu : ((1u << KT::PER_THREAD) - 1));
+    if (KB == 8 && !dh && a.hi_only && full) {
+      // lane-private cumulative counters: n_ge[r] = keys at or above splitter r (one 32-bit compare each); the
+      // records per destination are their differences
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const uint32_t h = (uint32_t)((unsigned long long)kt.u[i] >> 32);
+#pragma unroll
+        for (int r = 0; r < 7; r++) n_ge[r] += h > a.hi_m1[r] ? 1u : 0u;
+      }
+      n_all += KT::PER_THREAD;
+      continue;
+    }
+    if (KB == 8 && dh && a.hi_only && full) {
+      // the overlapped exchange's common case: seven 32-bit compares for the destination, one shift pair for the
+      // digit, one shared-memory atomic (the records per destination are the sums of its histogram)
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const unsigned long long u = (unsigned long long)kt.u[i];
+        const uint32_t h = (uint32_t)(u >> 32);
+        uint32_t d = 0;
+#pragma unroll
+        for (int r = 0; r < 7; r++) d += h > a.hi_m1[r] ? 1u : 0u;
+        atomicAdd(&sdh[d * RADIX + ((uint32_t)((u << a.digit_lshift[d]) >> a.digit_shift[d]) & (RADIX - 1))], 1u);
+      }
+      continue;
+    }
     const bool vec = dense && base + KT::TILE <= a.n;  // KeyTile's vector layout: thread t holds keys (j*THREADS+t)*VEC+e
 #pragma unroll
     for (int i = 0; i < KT::PER_THREAD; i++) {
@@ -271,8 +303,10 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
       const unsigned long long u = (unsigned long long)kt.u[i];
       const uint32_t d = v ? part_dest(u, idx, a.part) : 0u;
       if (a.world <= 8) {
+        if (!(dh && a.hi_only)) {  // (hi_only: the records per destination are taken from the histogram sums)
 #pragma unroll
-        for (int r = 0; r < 8; r++) cnt[r] += (v && d == (uint32_t)r) ? 1u : 0u;
+          for (int r = 0; r < 8; r++) cnt[r] += (v && d == (uint32_t)r) ? 1u : 0u;
+        }
         if (dh && v) atomicAdd(&sdh[d * RADIX + ((uint32_t)((u << a.digit_lshift[d]) >> a.digit_shift[d]) & (RADIX - 1))], 1u);
       } else {
         const unsigned vmask = __ballot_sync(0xffffffffu, v);
@@ -283,7 +317,7 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
   if (a.world <= 8) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      uint32_t c = cnt[r];
+      uint32_t c = cnt[r] + (r == 0 ? n_all : n_ge[r - 1]) - (r < 7 ? n_ge[r] : 0u);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh[r], c);
@@ -297,7 +331,10 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
   if (dh)
     for (int i = threadIdx.x; i < a.world * RADIX; i += HIST_THREADS) {
       const uint32_t c = sdh[i];
-      if (c) atomicAdd(&a.digit_hist[i], c);
+      if (c) {
+        atomicAdd(&a.digit_hist[i], c);
+        if (a.hi_only) atomicAdd(&a.counts[i / RADIX], (unsigned long long)c);  // (the fast path keeps no separate counters)
+      }
     }
 }
 
@@ -959,7 +996,16 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
   }
   CUDA_TRY(cudaMemcpyAsync(c->d_split_key, split_key.data(), sizeof(unsigned long long) * std::max(ns, 1), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(c->d_split_blk, split_blk.data(), sizeof(uint32_t) * std::max(ns, 1), cudaMemcpyHostToDevice, stream));
-  PartArgs part{c->d_split_key, c->d_split_blk, ns, blk_shift, has_tie ? 1 : 0};
+  PartArgs part{c->d_split_key, c->d_split_blk, ns, blk_shift, has_tie ? 1 : 0, 0u, {}};
+  part.hi_only = (kb == 8 && !has_tie && world <= 8) ? 1u : 0u;
+  for (int r = 0; r < 7; r++) {
+    part.hi_m1[r] = 0xffffffffu;
+    if (r < ns) {
+      const unsigned long long kv = split_key[r];
+      if ((uint32_t)kv != 0 || (kv >> 32) == 0) part.hi_only = 0;  // (a splitter at 0 or with low bits: general form)
+      else part.hi_m1[r] = (uint32_t)(kv >> 32) - 1u;
+    }
+  }
 
   // Overlapped exchange (the headline shape): full-width 8-byte keys, close to uniform, one box, peer memory.
   // Then every destination's local plan is known in advance (hybrid: the four -- or five -- digit positions
@@ -1033,6 +1079,8 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
       CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
     } else {
       for (int r = 0; r < world; r++) { da.digit_lshift[r] = d_lshift[r]; da.digit_shift[r] = d_cut[r] * RADIX_BITS; }
+      da.hi_only = part.hi_only;
+      for (int r = 0; r < 8; r++) da.hi_m1[r] = r < 7 ? part.hi_m1[r] : 0xffffffffu;
       for (int ch = 0; ch < n_chunks; ch++) {
         // (sweep tiles are a multiple of the counting kernel's tiles: 4096 vs 2048 keys)
         da.counts = my_slot->chunk_counts[ch];  // [8] used, the kernel's [RADIX] view stays inside the blob
@@ -1132,8 +1180,9 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
     if (p2p && landing)
       for (size_t s2 = 0; s2 < streams.size(); s2++) wa.ss.streams[s2].buf[1] = ws + L.land_off[s2];
     wa.bin_base = c->d_bin_base + (size_t)pass * RADIX; wa.lookback = lookback;
-    wa.tile_counter = tile_counter; wa.plan = c->d_plan; wa.tag = (uint32_t)pass + 1; wa.stage_bytes = stage_bytes;
-    wa.part = part; wa.lut_world = world; wa.tile_first = (uint32_t)t_first;
+    // (look-back tags 16.. : the local sort's passes, tags 1..8, reuse the same table later)
+    wa.tile_counter = tile_counter; wa.plan = c->d_plan; wa.tag = 16u + (uint32_t)pass; wa.stage_bytes = stage_bytes;
+    wa.part = part; wa.lut_world = world; wa.tile_first = (uint32_t)t_first; wa.peer_wide = opt_mgpu_wide.load() != 0 ? 1u : 0u;
     wa.peer_delta = p2p ? c->d_peer_delta : nullptr;
     return wa;
   };
@@ -1247,6 +1296,16 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
   }
   CUDA_TRY(cudaEventRecord(c->ev_fork, stream));
   CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  // (trace: when each chunk's partition kernel, arrival and first-pass kernels finished, relative to the fork)
+  std::vector<std::pair<std::string, cudaEvent_t>> tl;
+  auto tl_mark = [&](const std::string &name, cudaStream_t st2) {
+    if (!trace.on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st2);
+    tl.emplace_back(name, e);
+  };
+  tl_mark("fork", stream);
   SignalArgs sg{};
   sg.world = world; sg.me = c->rank;
   for (int r = 0; r < world; r++) sg.peer_flags[r] = (uint32_t *)((unsigned char *)c->peer_base[r] + L.flags_off);
@@ -1260,10 +1319,12 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
     mgpu_signal_kernel<<<1, 32, 0, stream>>>(sg);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    tl_mark("sent" + std::to_string(ch), stream);
     // receiver side of the same chunk
     mgpu_wait_kernel<<<1, 32, 0, c->side>>>((const uint32_t *)(ws + L.flags_off), world, ch, epoch + (uint32_t)ch + 1u);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    tl_mark("arrived" + std::to_string(ch), c->side);
     int64_t tiles_before = 0;
     for (int c2 = 0; c2 < ch; c2++)
       for (int s2 = 0; s2 < world; s2++) tiles_before += ((int64_t)blobs[s2].chunk_counts[c2][c->rank] + tile - 1) / tile;
@@ -1285,10 +1346,14 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
         wa.lookback = (uint64_t *)(ws + L.jtable_off) + (size_t)tiles_before * RADIX;
         wa.tile_counter = c->d_cons_ctr; wa.plan = c->d_plan; wa.tag = my_cut + 1; wa.stage_bytes = stage_bytes;
         wa.plan_in_args = 1; wa.arg_sel = 0; wa.arg_next_p1 = my_cut + 2; wa.arg_next_skewed = 0; wa.arg_sub = 0; wa.arg_lshift = my_lshift;
-        CUDA_TRY(launch_sweep(kb, cfg, wa, tiles_here, di.smem_optin, di.sm_count, c->side, /*first_pass_unordered=*/true));
+        // (high-priority stream: without a bound on its CTAs per SM the first pass would take every slot that frees
+        //  up and starve the partition kernel -- measured: the two then simply alternate)
+        CUDA_TRY(launch_sweep(kb, cfg, wa, tiles_here, di.smem_optin, di.sm_count, c->side, /*first_pass_unordered=*/true,
+                              (size_t)std::max<int64_t>(opt_mgpu_cons_smem_kb.load(), 0) << 10));
       }
       tiles_before += tiles_here;
     }
+    tl_mark("swept" + std::to_string(ch), c->side);
   }
   CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
   CUDA_TRY(cudaStreamWaitEvent(stream, c->ev_join, 0));
@@ -1305,6 +1370,19 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
     if (rc != 0) return rc;
   }
   trace.mark("local_sort_rest");
+  if (trace.on) {
+    cudaStreamSynchronize(stream);
+    std::string line = "[b200sort mgpu rank " + std::to_string(c->rank) + "] timeline (ms after the fork):";
+    for (size_t i = 1; i < tl.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tl[0].second, tl[i].second);
+      char buf[64];
+      snprintf(buf, sizeof buf, " %s=%.2f", tl[i].first.c_str(), ms);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (auto &e : tl) cudaEventDestroy(e.second);
+  }
   trace.report(c->rank);
   return 0;
 }

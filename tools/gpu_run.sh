@@ -33,7 +33,7 @@ for st in "$@"; do
     pytest) timeout 1500 python -m pytest $rest -x -q >> "$log" 2>&1 ;;
     py) t=${rest%%:*}; args=${rest#*:}; timeout $t python $args >> "$log" 2>&1 ;;
     mbench) n=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
-            B200SORT_MGPU_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n $args >> "$log" 2>&1 ;;
+            B200SORT_MGPU_TRACE=1 timeout 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n $args >> "$log" 2>&1 ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${name}_launches.csv python bench.py $rest >> "$log" 2>&1 ;;
     ncu) k=${rest%%:*}; r2=${rest#*:}; skip=${r2%%:*}; args=${r2#*:}
          timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/${name}_$k $SB $args >> "$log" 2>&1 ;;
