@@ -51,10 +51,11 @@ static std::atomic<int64_t> opt_host_pipeline{1};  // host SoA arrays: sort keys
 static std::atomic<int64_t> opt_mgpu_landing{1};  // multi-GPU: receive into a third set of arrays (saves the final copy)
 static std::atomic<int64_t> opt_mgpu_p2p{1};  // multi-GPU: scatter straight into peer memory (0: NCCL send/recv)
 static std::atomic<int64_t> opt_mgpu_refine{1};   // multi-GPU: refine heavy splitter bins / split heavy key values (0: fail with ENOMEM)
-static std::atomic<int64_t> opt_mgpu_overlap{1};  // multi-GPU: chunked exchange overlapped with the receivers' first pass
+static std::atomic<int64_t> opt_mgpu_overlap{0};  // multi-GPU: chunked exchange overlapped with the receivers' first pass (measured: no gain)
 static std::atomic<int64_t> opt_mgpu_chunks{4};   // ... in this many chunks
 static std::atomic<int64_t> opt_mgpu_wide{1};     // multi-GPU: 16-byte peer stores of element pairs
-static std::atomic<int64_t> opt_mgpu_cons_smem_kb{80};  // overlapped first pass: shared memory requested per CTA (80 KB: at most two per SM)
+static std::atomic<int64_t> opt_mgpu_cons_smem_kb{0};   // overlapped first pass: shared memory requested per CTA (bounds its CTAs per SM; 0 = what it needs)
+static std::atomic<int64_t> opt_mgpu_persist_x2{0};     // overlapped exchange: CTAs per SM of the looping partition kernel, times two
 static std::atomic<int64_t> opt_mgpu_chunk_min_log2{24};  // ... when a rank holds at least 2^this records
 static std::atomic<int64_t> opt_host_plan_min_log2{24};  // hybrid sorts of at least 2^this records read the plan back
 
@@ -168,7 +169,7 @@ inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
 // smem_floor: request at least this much dynamic shared memory (bounds how many CTAs of this launch an SM holds:
 // the overlapped first pass of the multi-GPU sort must leave room for the partition kernel's CTAs)
 static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_tiles, size_t smem_optin, int sm_count, cudaStream_t st,
-                                bool first_pass_unordered = false, size_t smem_floor = 0) {
+                                bool first_pass_unordered = false, size_t smem_floor = 0, int64_t grid_cap = 0) {
   bool any = false;  // a stream with 1- or 2-byte chunks in the move loop needs the ANYCHUNK instantiation
   int n_cols = 0;
   const bool soa = a.ss.streams[0].chunk_bytes * a.ss.streams[0].chunks_per_elem == (uint32_t)kb;
@@ -205,7 +206,8 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   if (e != cudaSuccess) return e;
   ProfScope ps(PK_SWEEP, st);
   (void)sm_count;
-  k<<<(unsigned)n_tiles, tc.threads, smem, st>>>(a2);
+  // (grid_cap: the partition pass of the overlapped exchange runs with fewer, looping CTAs)
+  k<<<(unsigned)(grid_cap > 0 ? std::min<int64_t>(n_tiles, grid_cap) : n_tiles), tc.threads, smem, st>>>(a2);
   g_launches++;
   return cudaGetLastError();
 }
@@ -1163,6 +1165,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "mgpu_chunks")) return &opt_mgpu_chunks;
   if (!strcmp(name, "mgpu_wide")) return &opt_mgpu_wide;
   if (!strcmp(name, "mgpu_cons_smem_kb")) return &opt_mgpu_cons_smem_kb;
+  if (!strcmp(name, "mgpu_persist_x2")) return &opt_mgpu_persist_x2;
   if (!strcmp(name, "mgpu_chunk_min_log2")) return &opt_mgpu_chunk_min_log2;
   if (!strcmp(name, "host_pipeline")) return &opt_host_pipeline;
   if (!strcmp(name, "junction_table")) return &opt_junction_table;

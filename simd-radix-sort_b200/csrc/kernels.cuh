@@ -719,6 +719,12 @@ struct SweepArgs {
   // tiles tile_first, tile_first + 1, ... (its tickets are relative to tile_first) up to record n
   uint32_t tile_first;
   uint32_t peer_wide;         // partition pass: 16-byte stores of element pairs into the destination arrays
+  // partition pass with arrival flags (overlapped exchange): tiles [sig_ct[c], sig_ct[c+1]) form chunk c
+  uint32_t sig_n;             // number of chunks (0: no signalling)
+  uint32_t sig_ct[9];
+  uint32_t *sig_done;         // [sig_n] tiles of each chunk delivered so far (zeroed)
+  uint32_t *sig_flags[8];     // flag arrays of the destinations: word [source * 8 + chunk]
+  uint32_t sig_me, sig_value; // this rank; the flag of chunk c is set to sig_value + c
   // ... and bucket d is written at byte offset peer_delta[d] from this GPU's own destination arrays: the
   // same array in the workspace of GPU d, mapped into this process (nullptr: everything stays local)
   const int64_t *peer_delta;
@@ -918,7 +924,7 @@ constexpr int RANK_BALLOT = 0, RANK_ATOMIC = 2;
 
 template <int KB, int THREADS, int IPT, int NSTAGE, bool ANYCHUNK, bool LUT, bool FIX, int RANK, bool BYTEWISE, bool FULL>
 __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *smem, const int64_t tile, const int n_valid,
-                                           const uint32_t sel, uint64_t *key_bar) {
+                                           const uint32_t sel, uint64_t *key_bar, const uint32_t key_parity) {
   constexpr int TILE = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
   using KeyT = typename UIntOf<KB>::type;
@@ -953,7 +959,7 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     // the tile was fetched by the bulk copy issued at kernel entry: wait for its bytes, then read the keys from
     // the staging buffer (consecutive lanes, consecutive keys: conflict-free).  The buffer is free again after
     // the barrier that follows the ranking, long before the bucket-ordered keys are staged into it.
-    mbar_wait(key_bar, 0);
+    mbar_wait(key_bar, key_parity);
     const KeyT *kt = reinterpret_cast<const KeyT *>(stage) + idx0;
 #pragma unroll
     for (int r = 0; r < IPT; r++) raw[r] = kt[r * 32];
@@ -1515,6 +1521,25 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     if (wr_s >= a.ss.n_streams) break;
     next_column(j);
   }
+  if constexpr (LUT) {
+    // Overlapped exchange: the destinations are told when a whole CHUNK of this rank's tiles has been delivered.
+    // Every thread makes its peer stores visible system-wide, then the tile is counted; whoever completes the
+    // chunk's count writes the chunk's arrival flag into every destination's flag array.
+    if (a.sig_n != 0) {
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t ch = 0;
+        while (ch + 1 < a.sig_n && (uint32_t)tile >= a.sig_ct[ch + 1]) ch++;
+        const uint32_t done = atomicAdd(&a.sig_done[ch], 1u) + 1u;
+        if (done == a.sig_ct[ch + 1] - a.sig_ct[ch]) {
+          __threadfence_system();
+          for (int d = 0; d < a.lut_world; d++)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.sig_flags[d] + a.sig_me * 8u + ch), "r"(a.sig_value + ch) : "memory");
+        }
+      }
+    }
+  }
 }
 
 // ANYCHUNK = false: every stream moved by the loop has 4-, 8- or 16-byte chunks (the common shapes).
@@ -1535,25 +1560,38 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
   // One tile per CTA.  (A persistent grid that loops over tickets was measured 17 % slower: CTAs that
   // start together stay in phase, so loads, look-backs and stores of the whole machine bunch up; fresh
   // CTAs per tile stagger naturally.  profiles/README.md)
+  // The partition pass of the multi-GPU sort (LUT) is the exception: it is bound by the NVLink, not by the SMs,
+  // and when its exchange is overlapped with the receivers' first pass it is launched with FEWER CTAs than
+  // tiles -- about one and a half per SM -- which loop over the tickets, so that the other kernel's CTAs find
+  // room on every SM the whole time (mgpu.cuh).
   __shared__ uint32_t s_tile;
   __shared__ __align__(8) uint64_t s_key_bar;
-  if (threadIdx.x == 0) {
-    const uint32_t t = atomicAdd(&a.tile_counter[a.pass], 1u) + a.tile_first;
-    s_tile = t;
-    if (a.tma_keys && a.n - (int64_t)t * TILE >= TILE) {
-      mbar_init(&s_key_bar, 1);
-      tma_load_tile(smem, a.ss.streams[0].buf[sel] + (size_t)t * TILE * KB, (uint32_t)(TILE * KB), &s_key_bar);
+  uint32_t key_parity = 0;
+  if (LUT && a.tma_keys && threadIdx.x == 0) mbar_init(&s_key_bar, 1);
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const uint32_t t = atomicAdd(&a.tile_counter[a.pass], 1u) + a.tile_first;
+      s_tile = t;
+      if (a.tma_keys && a.n - (int64_t)t * TILE >= TILE) {
+        if (!LUT) mbar_init(&s_key_bar, 1);
+        tma_load_tile(smem, a.ss.streams[0].buf[sel] + (size_t)t * TILE * KB, (uint32_t)(TILE * KB), &s_key_bar);
+      }
     }
+    for (int i = threadIdx.x; i < RANK_WORDS / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t remaining = a.n - tile * TILE;
+    if (LUT && remaining <= 0) break;  // (looping CTAs: the tickets are used up)
+    if (remaining >= TILE) {
+      sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK, BYTEWISE, true>(a, smem, tile, TILE, sel, &s_key_bar, key_parity);
+      if (a.tma_keys) key_parity ^= 1u;
+    } else {
+      sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK_BALLOT, BYTEWISE, false>(a, smem, tile, (int)remaining, sel, &s_key_bar, key_parity);
+    }
+    if (!LUT) break;
+    __syncthreads();  // everyone is done with the tile's shared memory before the next ticket is drawn
   }
-  for (int i = threadIdx.x; i < RANK_WORDS / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
-  __syncthreads();
-  const int64_t tile = s_tile;
-  const int64_t remaining = a.n - tile * TILE;
-  if (remaining >= TILE)
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK, BYTEWISE, true>(a, smem, tile, TILE, sel, &s_key_bar);
-  else
-    sweep_tile<KB, THREADS, IPT, NSTAGE, ANYCHUNK, LUT, FIX, RANK_BALLOT, BYTEWISE, false>(a, smem, tile, (int)remaining, sel, &s_key_bar);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -338,13 +338,84 @@ __global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_
     }
 }
 
+// The fast forms of dest_count_kernel as a kernel of their own (8-byte keys, splitters with zero low words, no
+// ties, full tiles only -- the caller sends the last, partial tile through the general kernel): the general
+// kernel's three code paths cost it registers and a third of its speed.
+template <int NLD>
+__global__ void __launch_bounds__(HIST_THREADS, 1024 / HIST_THREADS) dest_count_fast_kernel(DestCountArgs a) {
+  using KT = KeyTile<8, HIST_THREADS, NLD>;
+  __shared__ uint32_t sdh[8 * RADIX];
+  const bool dh = a.digit_hist != nullptr;
+  if (dh)
+    for (int i = threadIdx.x; i < 8 * RADIX; i += HIST_THREADS) sdh[i] = 0;
+  __syncthreads();
+  uint32_t n_ge[7] = {0, 0, 0, 0, 0, 0, 0}, n_all = 0;
+  for (int64_t tile = a.tile_lo + blockIdx.x; tile < a.tile_hi; tile += gridDim.x) {
+    KT kt;
+    kt.template load<false>(a.keys, a.stride, a.n, tile, a.ko);  // (full tiles: every key valid)
+    if (dh) {
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const unsigned long long u = (unsigned long long)kt.u[i];
+        const uint32_t h = (uint32_t)(u >> 32);
+        uint32_t d = 0;
+#pragma unroll
+        for (int r = 0; r < 7; r++) d += h > a.hi_m1[r] ? 1u : 0u;
+        atomicAdd(&sdh[d * RADIX + ((uint32_t)((u << a.digit_lshift[d]) >> a.digit_shift[d]) & (RADIX - 1))], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KT::PER_THREAD; i++) {
+        const uint32_t h = (uint32_t)((unsigned long long)kt.u[i] >> 32);
+#pragma unroll
+        for (int r = 0; r < 7; r++) n_ge[r] += h > a.hi_m1[r] ? 1u : 0u;
+      }
+      n_all += KT::PER_THREAD;
+    }
+  }
+  if (dh) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.world * RADIX; i += HIST_THREADS) {
+      const uint32_t c = sdh[i];
+      if (c) {
+        atomicAdd(&a.digit_hist[i], c);
+        atomicAdd(&a.counts[i / RADIX], (unsigned long long)c);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t c = (r == 0 ? n_all : n_ge[r - 1]) - (r < 7 ? n_ge[r] : 0u);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if ((threadIdx.x & 31) == 0 && r < a.world && c) atomicAdd(&a.counts[r], (unsigned long long)c);
+    }
+  }
+}
+
 static cudaError_t launch_dest_count(int kb, const DestCountArgs &a0, int sm_count, cudaStream_t st) {
   DestCountArgs a = a0;
   const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
   const int64_t n_tiles = (a.n + tile_keys - 1) / tile_keys;
   if (a.tile_hi <= 0 || a.tile_hi > n_tiles) a.tile_hi = n_tiles;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.tile_hi - a.tile_lo, (int64_t)sm_count * 8));
   ProfScope ps(PK_HIST, st);
+  const bool dense = a.stride == (uint32_t)kb && (((uintptr_t)a.keys) & 15) == 0;
+  if (kb == 8 && a.hi_only && a.world <= 8 && dense) {
+    // full tiles through the lean kernel, a partial last tile (if it belongs to this launch) through the general one
+    const int64_t full_hi = std::min<int64_t>(a.tile_hi, a.n / tile_keys);
+    if (full_hi > a.tile_lo) {
+      DestCountArgs f = a;
+      f.tile_hi = full_hi;
+      const int gridf = (int)std::max<int64_t>(1, std::min<int64_t>(full_hi - a.tile_lo, (int64_t)sm_count * 4));
+      dest_count_fast_kernel<hist_nld(8)><<<gridf, HIST_THREADS, 0, st>>>(f);
+      g_launches++;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+    if (full_hi >= a.tile_hi) return cudaSuccess;
+    a.tile_lo = std::max(a.tile_lo, full_hi);
+  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.tile_hi - a.tile_lo, (int64_t)sm_count * 8));
   switch (kb) {
     case 1: dest_count_kernel<1, hist_nld(1)><<<grid, HIST_THREADS, 0, st>>>(a); break;
     case 2: dest_count_kernel<2, hist_nld(2)><<<grid, HIST_THREADS, 0, st>>>(a); break;
@@ -686,7 +757,7 @@ int b200sort_mgpu_comm_create(b200sort_comm **out, int world_size, int rank, con
   CUDA_TRY(cudaMalloc(&c->d_split_blk, sizeof(uint32_t) * RADIX));
   CUDA_TRY(cudaMalloc(&c->d_bin_base, sizeof(uint64_t) * RADIX * MGPU_MAX_CHUNKS));
   CUDA_TRY(cudaMalloc(&c->d_cons_base, sizeof(uint64_t) * RADIX * MGPU_MAX_CHUNKS * 8));
-  CUDA_TRY(cudaMalloc(&c->d_cons_ctr, sizeof(uint32_t) * MGPU_MAX_CHUNKS * 8));
+  CUDA_TRY(cudaMalloc(&c->d_cons_ctr, sizeof(uint32_t) * (MGPU_MAX_CHUNKS * 8 + MGPU_MAX_CHUNKS)));  // (+ the chunks' delivery counters)
   CUDA_TRY(cudaMalloc(&c->d_plan, sizeof(Plan)));
   CUDA_TRY(cudaMalloc(&c->d_peer_delta, sizeof(int64_t) * RADIX));
   CUDA_TRY(cudaMalloc(&c->d_tie_less, sizeof(unsigned long long) * MGPU_MAX_REFINE * (size_t)(world_size + 1)));
@@ -1074,6 +1145,8 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
   if (num_local > 0) {
     DestCountArgs da{};
     da.keys = keys; da.stride = kstride; da.n = num_local; da.ko = ko; da.part = part; da.world = world;
+    da.hi_only = part.hi_only;
+    for (int r = 0; r < 8; r++) da.hi_m1[r] = r < 7 ? part.hi_m1[r] : 0xffffffffu;
     if (!overlap) {
       da.counts = my_slot->counts; da.tile_lo = 0; da.tile_hi = 0;
       CUDA_TRY(launch_dest_count(kb, da, di.sm_count, stream));
@@ -1290,7 +1363,7 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
         for (int d = 0; d < RADIX; d++) { cb[(size_t)Lx * RADIX + d] = run[d]; run[d] += blobs[s2].chunk_hist[ch][c->rank][d]; }
       }
     CUDA_TRY(cudaMemcpyAsync(c->d_cons_base, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemsetAsync(c->d_cons_ctr, 0, sizeof(uint32_t) * MGPU_MAX_CHUNKS * 8, stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_cons_ctr, 0, sizeof(uint32_t) * (MGPU_MAX_CHUNKS * 8 + MGPU_MAX_CHUNKS), stream));
     // the first pass's look-back table: the junction table's memory (unused until the last pass)
     CUDA_TRY(cudaMemsetAsync(ws + L.jtable_off, 0, (size_t)L.n_tiles * RADIX * 8, stream));
   }
@@ -1310,16 +1383,55 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
   sg.world = world; sg.me = c->rank;
   for (int r = 0; r < world; r++) sg.peer_flags[r] = (uint32_t *)((unsigned char *)c->peer_base[r] + L.flags_off);
   const uint32_t epoch = c->seq * 16u;
-  for (int ch = 0; ch < n_chunks; ch++) {
-    if (ct[ch + 1] > ct[ch]) {
+  // ONE partition kernel for all chunks, launched with about one and a half CTAs per SM that loop over the tile
+  // tickets (so that the first-pass kernels of the side stream find room on every SM the whole time); the CTA
+  // that delivers the last tile of a chunk writes the chunk's arrival flag into every destination's flag array.
+  // (A chunk without tiles is signalled from here.)
+  for (int ch = 0; ch < n_chunks; ch++)
+    if (ct[ch + 1] == ct[ch]) {
+      sg.chunk = ch; sg.value = epoch + (uint32_t)ch + 1u;
+      mgpu_signal_kernel<<<1, 32, 0, stream>>>(sg);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+  const int64_t persist_x2 = opt_mgpu_persist_x2.load();
+  if (persist_x2 <= 0) {
+    // variant: one ordinary partition kernel per chunk (one CTA per tile), each followed by a one-warp kernel
+    // that writes the chunk's flags (the first-pass kernels of the high-priority side stream then alternate with
+    // the chunks' partition kernels rather than run beside them)
+    std::vector<uint64_t> bb((size_t)n_chunks * RADIX, 0);
+    for (int r = 0; r < world; r++) {
+      int64_t o = 0;
+      for (int s2 = 0; s2 < c->rank; s2++) o += (int64_t)m(s2, r);
+      for (int ch = 0; ch < n_chunks; ch++) {
+        bb[(size_t)ch * RADIX + r] = (uint64_t)o;
+        o += (int64_t)blobs[c->rank].chunk_counts[ch][r];
+      }
+    }
+    for (int ch = 0; ch < n_chunks; ch++)
+      for (int r = world; r < RADIX; r++) bb[(size_t)ch * RADIX + r] = (uint64_t)num_local;
+    CUDA_TRY(cudaMemcpyAsync(c->d_bin_base, bb.data(), bb.size() * 8, cudaMemcpyHostToDevice, stream));
+    for (int ch = 0; ch < n_chunks; ch++) {
+      if (ct[ch + 1] == ct[ch]) continue;  // (signalled above)
       SweepArgs wa = partition_args(ch, ct[ch], std::min<int64_t>(num_local, ct[ch + 1] * tile));
       CUDA_TRY(launch_sweep(kb, cfg, wa, ct[ch + 1] - ct[ch], di.smem_optin, di.sm_count, stream));
+      sg.chunk = ch; sg.value = epoch + (uint32_t)ch + 1u;
+      mgpu_signal_kernel<<<1, 32, 0, stream>>>(sg);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
     }
-    sg.chunk = ch; sg.value = epoch + (uint32_t)ch + 1u;
-    mgpu_signal_kernel<<<1, 32, 0, stream>>>(sg);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    tl_mark("sent" + std::to_string(ch), stream);
+  } else if (n_tiles_local > 0) {
+    SweepArgs wa = partition_args(0, 0, num_local);
+    wa.sig_n = (uint32_t)n_chunks;
+    for (int ch = 0; ch <= n_chunks; ch++) wa.sig_ct[ch] = (uint32_t)ct[ch];
+    wa.sig_done = c->d_cons_ctr + MGPU_MAX_CHUNKS * 8;
+    for (int r = 0; r < world; r++) wa.sig_flags[r] = sg.peer_flags[r];
+    wa.sig_me = (uint32_t)c->rank; wa.sig_value = epoch + 1u;
+    const int64_t cap = std::max<int64_t>(1, (int64_t)di.sm_count * persist_x2 / 2);
+    CUDA_TRY(launch_sweep(kb, cfg, wa, n_tiles_local, di.smem_optin, di.sm_count, stream, false, 0, cap));
+  }
+  tl_mark("sent_all", stream);
+  for (int ch = 0; ch < n_chunks; ch++) {
     // receiver side of the same chunk
     mgpu_wait_kernel<<<1, 32, 0, c->side>>>((const uint32_t *)(ws + L.flags_off), world, ch, epoch + (uint32_t)ch + 1u);
     g_launches++;

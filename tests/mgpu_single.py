@@ -55,11 +55,13 @@ def main():
     run(O.make_keys("Uniform", np.uint64, n, 3), True, "landing u64", 0)
     S.set_option("mgpu_chunk_min_log2", 12)
     S.set_option("mgpu_overlap", 2)   # 2: also with a world of one (this vehicle)
-    for chunks in (4, 1, 3):
+    for chunks, persist in ((4, 0), (1, 3), (3, 4), (8, 2)):
         S.set_option("mgpu_chunks", chunks)
+        S.set_option("mgpu_persist_x2", persist)
         run(O.make_keys("Uniform", np.uint64, n, 4 + chunks), True, f"overlap u64 chunks={chunks}", 1)
         run(O.make_keys("Uniform", np.int64, n, 14 + chunks), False, f"overlap i64 desc chunks={chunks}", 1)
-    S.set_option("mgpu_overlap", 1)
+    S.set_option("mgpu_overlap", 0)
+    S.set_option("mgpu_persist_x2", 0)
     S.set_option("mgpu_chunk_min_log2", 24)
     S.set_option("mgpu_chunks", 4)
     run(np.zeros(n, np.int64), True, "zero")

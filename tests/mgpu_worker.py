@@ -157,9 +157,11 @@ def main():
     # ---- overlapped exchange: chunked partition kernels, arrival flags, first pass of the receivers chunk by chunk ----
     S.set_option("host_plan_min_log2", 0)      # landing arrays at test size
     S.set_option("mgpu_chunk_min_log2", 12)
+    S.set_option("mgpu_overlap", 1)            # (off by default: DESIGN.md section 5)
     L.b200sort_mgpu_used_overlap.argtypes = [ctypes.c_void_p]
-    for n_chunks in (4, 3, 1):
+    for n_chunks, persist in ((4, 0), (3, 3), (8, 4), (1, 0)):
         S.set_option("mgpu_chunks", n_chunks)
+        S.set_option("mgpu_persist_x2", persist)   # 0: one partition kernel per chunk; else looping CTAs, persist/2 per SM
         for dt, up in ((np.uint64, True), (np.int64, False), (np.uint64, False)):
             n_loc = (1 << 19) + 4099 + 77 * rank
             keys = O.make_keys("Uniform", dt, n_loc, seed=500 + rank + n_chunks)
@@ -182,6 +184,8 @@ def main():
     S.set_option("host_plan_min_log2", 24)
     S.set_option("mgpu_chunk_min_log2", 24)
     S.set_option("mgpu_chunks", 4)
+    S.set_option("mgpu_overlap", 0)
+    S.set_option("mgpu_persist_x2", 0)
     dist.barrier()
     assert L.b200sort_mgpu_comm_destroy(comm) == 0
     dist.destroy_process_group()

@@ -534,6 +534,7 @@ def test_cmp_sorter_none_partial_sort_contract(thresh):
     rng = np.random.default_rng(thresh)
     CMP_NONE = 1
     try:
+        S.set_option("algo", 2)           # (the MSB hybrid path is the default from 2^22 records)
         S.set_option("host_plan_min_log2", 0)
         S.set_option("margin_bits", -2)   # about four keys per final segment: plenty of unordered small buckets
         for dt, up in ((np.uint64, True), (np.int64, False), (np.float64, True)):
@@ -578,5 +579,6 @@ def test_cmp_sorter_none_partial_sort_contract(thresh):
         assert _within_thresh_of_sorted(O.order_key(ok, True), O.order_key(np.sort(ok), True), 32)
         assert out.tobytes() == O.make_records(ok, 16).tobytes()   # records stayed whole
     finally:
+        S.set_option("algo", 0)
         S.set_option("host_plan_min_log2", 24)
         S.set_option("margin_bits", 2)
