@@ -22,8 +22,18 @@
  *  - return value: 0 on success, a negative B200SORT_E* code otherwise; b200sort_last_error() gives
  *    a thread-local human-readable message.  There is NO CPU fallback: without a usable CUDA device
  *    every sort call fails with B200SORT_ECUDA.
- *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device-memory
- *    calls are asynchronous on that stream; host-memory calls return after the data is back.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Host-memory calls
+ *    return after the data is back.  Device-memory calls are ordered on that stream; whether the call
+ *    itself waits for the device depends on the size:
+ *      * fewer than 2^24 records, keys of <= 4 bytes (or 8-byte keys below 2^22 records): asynchronous;
+ *      * 8-byte keys from 2^22 records (MSB hybrid plan): returns when the sort is complete (one wait at
+ *        the end: the device-made plan may ask the host for the digit-by-digit fall-back);
+ *      * any sort of >= 2^24 records: additionally waits once, early, for the 200-byte pass plan made
+ *        on the device, so that only the passes that execute are launched.
+ *    These calls therefore cannot be captured into a CUDA graph; everything between the two waits
+ *    (all passes, the junction kernel, the flag-gated segment finish / copy-back) is queued without one.
+ *  - device arrays are sorted on the device that owns them, whatever the caller's current device is;
+ *    all arrays of one call must live on the same device.
  */
 #ifndef B200SORT_H_
 #define B200SORT_H_
@@ -78,7 +88,9 @@ int b200sort_sort_aos(void *records, int key_type, uint32_t record_bytes, int64_
  * threshold (as in the reference).  With B200SORT_CMP_NONE the result satisfies the reference's
  * partial-sort contract: the array is a permutation of the input in which every maximal group of
  * elements sharing the key bits above the point where the reference would stop recursing is
- * contiguous and groups appear in key order. */
+ * contiguous and groups appear in key order.  (Thresholds below 8 give the full sort: nearly every input would
+ * need the finish anyway.  From 8 on, the digit sweeps run, a key-only sweep checks that no group longer than the
+ * threshold is out of order -- only then does the segment finish run.) */
 int b200sort_sort_soa_ex(void *keys, int key_type, int64_t num, int ascending, int n_payloads,
                          void *const *payloads, const uint32_t *payload_elem_bytes,
                          int64_t cmp_sort_threshold, int cmp_sorter, void *stream, void *workspace,
