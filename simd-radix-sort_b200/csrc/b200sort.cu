@@ -217,34 +217,45 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
 }
 
 constexpr int HIST_THREADS = 256;  // key-only sweeps: 256 threads x NLD x 16 B per tile, 4 CTAs per SM
-constexpr int hist_nld(int kb) { return kb == 1 ? 2 : 4; }  // at most 32 keys per thread
+constexpr int hist_nld(int kb) { return kb == 1 ? 2 : (kb >= 4 ? 8 : 4); }  // at most 32 keys per thread; 128 bytes in flight per thread for 8-byte keys
 
-template <int KB>
+template <int KB, int NLD>
 static cudaError_t launch_hist_t(const HistArgs &a, int grid, bool use_match, int probe, cudaStream_t st) {
   ProfScope ps(PK_HIST, st);
   if (probe == 2) {
-    minmax_kernel<KB, HIST_THREADS, hist_nld(KB)><<<grid, HIST_THREADS, 0, st>>>(a);
+    minmax_kernel<KB, HIST_THREADS, NLD><<<grid, HIST_THREADS, 0, st>>>(a);
   } else if (probe) {
-    if (use_match) probe_kernel<KB, HIST_THREADS, hist_nld(KB), true><<<grid, HIST_THREADS, 0, st>>>(a);
-    else probe_kernel<KB, HIST_THREADS, hist_nld(KB), false><<<grid, HIST_THREADS, 0, st>>>(a);
+    if (use_match) probe_kernel<KB, HIST_THREADS, NLD, true><<<grid, HIST_THREADS, 0, st>>>(a);
+    else probe_kernel<KB, HIST_THREADS, NLD, false><<<grid, HIST_THREADS, 0, st>>>(a);
   } else {
-    if (use_match) hist_kernel<KB, HIST_THREADS, hist_nld(KB), true><<<grid, HIST_THREADS, 0, st>>>(a);
-    else hist_kernel<KB, HIST_THREADS, hist_nld(KB), false><<<grid, HIST_THREADS, 0, st>>>(a);
+    if (use_match) hist_kernel<KB, HIST_THREADS, NLD, true><<<grid, HIST_THREADS, 0, st>>>(a);
+    else hist_kernel<KB, HIST_THREADS, NLD, false><<<grid, HIST_THREADS, 0, st>>>(a);
   }
   g_launches++;
   return cudaGetLastError();
 }
 
+// keys per tile of the key-only sweeps over this key array
+static int64_t hist_tile_keys(int kb, const void *keys, uint32_t stride) {
+  // (8-byte keys in a dense, 16-byte aligned array: eight 16-byte vectors in flight per thread -- probe 1.66 ->
+  //  1.33 ms at 1e9 keys; records with the key inside are read one key per load, where more per thread is slower)
+  const bool dense = stride == (uint32_t)kb && (((uintptr_t)keys) & 15) == 0;
+  const int nld = (kb == 8 && !dense) ? 4 : hist_nld(kb);  // (4-byte keys: 8 vectors = 32 keys per thread either way)
+  return (int64_t)HIST_THREADS * nld * (16 / kb);
+}
+
 cudaError_t launch_hist(int kb, const HistArgs &a, int sm_count, int probe, cudaStream_t st) {
-  const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
+  const int64_t tile_keys = hist_tile_keys(kb, a.keys, a.stride);
   const int64_t tiles = (a.n + tile_keys - 1) / tile_keys;
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * 8);
   const bool m = opt_hist_match.load() != 0;
   switch (kb) {
-    case 1: return launch_hist_t<1>(a, grid, m, probe, st);
-    case 2: return launch_hist_t<2>(a, grid, m, probe, st);
-    case 4: return launch_hist_t<4>(a, grid, m, probe, st);
-    default: return launch_hist_t<8>(a, grid, m, probe, st);
+    case 1: return launch_hist_t<1, hist_nld(1)>(a, grid, m, probe, st);
+    case 2: return launch_hist_t<2, hist_nld(2)>(a, grid, m, probe, st);
+    case 4: return launch_hist_t<4, hist_nld(4)>(a, grid, m, probe, st);
+    default:
+      return tile_keys == (int64_t)HIST_THREADS * 4 * 2 ? launch_hist_t<8, 4>(a, grid, m, probe, st)
+                                                        : launch_hist_t<8, hist_nld(8)>(a, grid, m, probe, st);
   }
 }
 
@@ -518,7 +529,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     ha.stride = streams[0].elem_bytes;
     ha.n = n; ha.ko = ko; ha.digit_mask = (1u << kb) - 1; ha.ghist = ghist; ha.probe = probe;
     {
-      const int64_t tile_keys = (int64_t)HIST_THREADS * hist_nld(kb) * (16 / kb);
+      const int64_t tile_keys = hist_tile_keys(kb, ha.keys, ha.stride);
       // entropies from one key per thread of every 16th tile (option probe_sample) once there are plenty of tiles
       const bool sparse = (n / tile_keys) >= 8192;
       ha.sample = sparse ? (uint32_t)std::max<int64_t>(1, opt_probe_sample.load()) : 1;
