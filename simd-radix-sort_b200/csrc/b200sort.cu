@@ -147,6 +147,7 @@ static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstag
 }
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
+static std::atomic<int64_t> opt_prefetch_cols{1};  // the tile's part of the payload columns is prefetched into L2 when the tile starts
 static std::atomic<int64_t> opt_tma_keys{1};      // key tiles arrive by one TMA bulk copy per tile (cp.async.bulk + mbarrier)
 static std::atomic<int64_t> opt_bytewise{1};      // lean kernels when the host knows the plan (no range reduction / shift)
 static std::atomic<int64_t> opt_first_atomic{1};  // first executed pass of a large sort: unstable atomicAdd ranking
@@ -211,6 +212,19 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   ProfScope ps(PK_SWEEP, st);
   (void)sm_count;
   // (grid_cap: the partition pass of the overlapped exchange runs with fewer, looping CTAs)
+  // L2 prefetch of the tile's part of the first column after the keys (16-byte aligned on both sides)
+  a2.prefetch_cols = 0;
+  {
+    const int s2 = a2.tma_keys ? 1 : 0;
+    if (opt_prefetch_cols.load() != 0 && s2 < a.ss.n_streams) {
+      const Stream &st2 = a.ss.streams[s2];
+      const size_t bytes = (size_t)tc.threads * tc.ipt * st2.chunk_bytes * st2.chunks_per_elem;
+      if ((((uintptr_t)st2.buf[0] | (uintptr_t)st2.buf[1] | bytes) & 15) == 0) {
+        a2.prefetch_cols = 1; a2.prefetch_bytes = (uint32_t)bytes;
+        a2.prefetch_ptr[0] = st2.buf[0]; a2.prefetch_ptr[1] = st2.buf[1];
+      }
+    }
+  }
   k<<<(unsigned)(grid_cap > 0 ? std::min<int64_t>(n_tiles, grid_cap) : n_tiles), tc.threads, smem, st>>>(a2);
   g_launches++;
   return cudaGetLastError();
@@ -1162,6 +1176,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "tile_cfg")) return &opt_tile_cfg;
   if (!strcmp(name, "first_atomic")) return &opt_first_atomic;
   if (!strcmp(name, "tma_keys")) return &opt_tma_keys;
+  if (!strcmp(name, "prefetch_cols")) return &opt_prefetch_cols;
   if (!strcmp(name, "bytewise")) return &opt_bytewise;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "allow_reduce")) return &opt_allow_reduce;

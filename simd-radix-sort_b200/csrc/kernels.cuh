@@ -739,6 +739,10 @@ struct SweepArgs {
   // the key tile of a full tile arrives by one TMA bulk copy (SoA keys, 16-byte aligned arrays), issued by the
   // kernel's first thread right after it has drawn the tile ticket
   uint32_t tma_keys;
+  // ... and the tile's part of every other column is prefetched into L2 at the same moment: the column pipeline
+  // only gets to load it after the key column has left the staging buffer, and then finds it in L2
+  uint32_t prefetch_cols, prefetch_bytes;       // (one column: the first one after the keys; bytes per tile)
+  const unsigned char *prefetch_ptr[2];         // its array on either side of the ping-pong
   uint32_t fix_cut;
   uint32_t *fix_flag;
   // ... and [n_tiles][RADIX] words {fingerprint of the swept bits of the first key | of the last key << 32} of
@@ -812,6 +816,10 @@ __device__ __forceinline__ void tma_load_tile(void *smem_dst, const void *gsrc, 
                    (uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(b)
                : "memory");
+}
+// L2 prefetch of a contiguous global range (cp.async.bulk.prefetch.L2): no shared memory, no completion to wait for
+__device__ __forceinline__ void tma_prefetch_l2(const void *gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
@@ -1100,6 +1108,8 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs &a, unsigned char *sm
     // shared-memory atomic by the leaders instead of a load by everyone plus a store by the leaders: the scatter
     // pass is bound by L1TEX/shared-memory wavefronts, and rows are issued in order, so the ranks stay stable.)
     const unsigned lt = lanemask_lt();
+    // (Ranking two or four rows at a time -- all ballots, then the leader atomics back to back, then the shuffles --
+    //  would overlap the atomic -> shuffle round trips, but exhausts the seven predicate registers: ptxas gives up.)
     auto rank_row = [&](int r, unsigned peers) {
       const uint32_t d = digit_of(r);
       const uint32_t lower = __popc(peers & lt);
@@ -1576,6 +1586,11 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const __grid_co
         if (!LUT) mbar_init(&s_key_bar, 1);
         tma_load_tile(smem, a.ss.streams[0].buf[sel] + (size_t)t * TILE * KB, (uint32_t)(TILE * KB), &s_key_bar);
       }
+      // (the host has checked alignment and sizes of streams prefetch_first .. prefetch_first + prefetch_cols - 1)
+      if (a.prefetch_cols != 0 && a.n - (int64_t)t * TILE >= TILE)
+        tma_prefetch_l2(a.prefetch_ptr[sel] + (size_t)t * a.prefetch_bytes, a.prefetch_bytes);
+      // (Prefetching the tile ~444 tickets further on as well -- what the CTAs in flight will draw next -- was
+      //  measured SLOWER: 37.5 vs 36.2 ms at 1e9 records, 38.4 with 1000 tickets: profiles/README.md.)
     }
     for (int i = threadIdx.x; i < RANK_WORDS / 4; i += THREADS) reinterpret_cast<uint4 *>(warp_cnt)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < RADIX; i += THREADS) nhist[i] = 0;
