@@ -148,6 +148,7 @@ static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstag
 
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
 static std::atomic<int64_t> opt_prefetch_cols{1};  // the tile's part of the payload columns is prefetched into L2 when the tile starts
+static std::atomic<int64_t> opt_max_chunk{16};     // largest chunk a stream is moved in (ablation: 8 = AoS records as 8-byte columns)
 static std::atomic<int64_t> opt_tma_keys{1};      // key tiles arrive by one TMA bulk copy per tile (cp.async.bulk + mbarrier)
 static std::atomic<int64_t> opt_bytewise{1};      // lean kernels when the host knows the plan (no range reduction / shift)
 static std::atomic<int64_t> opt_first_atomic{1};  // first executed pass of a large sort: unstable atomicAdd ranking
@@ -461,7 +462,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
   StreamSet ss{};
   ss.n_streams = (int)streams.size();
   for (size_t s = 0; s < streams.size(); s++) {
-    const uint32_t c = chunk_for(streams[s].ptr, streams[s].elem_bytes);
+    const uint32_t c = std::min<uint32_t>(chunk_for(streams[s].ptr, streams[s].elem_bytes), (uint32_t)std::max<int64_t>(opt_max_chunk.load(), 1));
     ss.streams[s].chunk_bytes = c;
     ss.streams[s].chunks_per_elem = streams[s].elem_bytes / c;
     ss.streams[s].buf[0] = (unsigned char *)streams[s].ptr;
@@ -659,7 +660,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     const bool soa = streams[0].elem_bytes == (uint32_t)kb;
     // partial-sort mode: no ordering of the final segments at all, only a check that none exceeds the threshold
     const bool partial = have_plan && hplan.cut_digit != 0 && xo.cmp_none_thresh >= CMP_NONE_MIN_THRESH;
-    const bool use_fix = !partial && have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes == 16) && cfg == kDefaultTileCfg && opt_fix_in_pass.load() != 0;
+    const bool use_fix = !partial && have_plan && hplan.cut_digit != 0 && (soa || ss.streams[0].chunk_bytes >= (uint32_t)kb) && cfg == kDefaultTileCfg && opt_fix_in_pass.load() != 0;
     int last_pass = -1;
     bool first_exec = true;
     if (landing && hplan.n_exec == 0) {  // nothing will move the records: deliver them
@@ -1177,6 +1178,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "first_atomic")) return &opt_first_atomic;
   if (!strcmp(name, "tma_keys")) return &opt_tma_keys;
   if (!strcmp(name, "prefetch_cols")) return &opt_prefetch_cols;
+  if (!strcmp(name, "max_chunk")) return &opt_max_chunk;
   if (!strcmp(name, "bytewise")) return &opt_bytewise;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;
   if (!strcmp(name, "allow_reduce")) return &opt_allow_reduce;
