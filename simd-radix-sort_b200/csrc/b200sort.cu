@@ -206,7 +206,7 @@ static cudaError_t launch_sweep(int kb, int cfg, const SweepArgs &a, int64_t n_t
   // cannot be resident on an SM together (the overlapped exchange runs two of them side by side)
   // (only for the kernels of the overlapped exchange: a maximal carve-out leaves the other sorts 28 KB of L1,
   //  which costs them 4 % -- 38.2 vs 36.8 ms at 1e9 records)
-  if (lut || smem_floor != 0 || grid_cap != 0 || opt_mgpu_overlap.load() != 0) {
+  if (smem_floor != 0 || grid_cap != 0 || opt_mgpu_overlap.load() != 0) {
     e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
   }
