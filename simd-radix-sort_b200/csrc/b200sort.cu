@@ -149,6 +149,7 @@ static size_t sweep_smem_bytes(const TileCfg &c, uint32_t stage_bytes, int nstag
 static std::atomic<int64_t> opt_nstage{0};  // 0 auto, 1 single staging buffer, 2 double-buffered columns
 static std::atomic<int64_t> opt_prefetch_cols{1};  // the tile's part of the payload columns is prefetched into L2 when the tile starts
 static std::atomic<int64_t> opt_max_chunk{16};     // largest chunk a stream is moved in (ablation: 8 = AoS records as 8-byte columns)
+static std::atomic<int64_t> opt_wide_tiles{1};    // 4-byte keys, all chunks <= 4 bytes: 8192-key tiles
 static std::atomic<int64_t> opt_tma_keys{1};      // key tiles arrive by one TMA bulk copy per tile (cp.async.bulk + mbarrier)
 static std::atomic<int64_t> opt_bytewise{1};      // lean kernels when the host knows the plan (no range reduction / shift)
 static std::atomic<int64_t> opt_first_atomic{1};  // first executed pass of a large sort: unstable atomicAdd ranking
@@ -161,6 +162,7 @@ inline SweepFn sweep_fn(int kb, int cfg, const SweepSel &s) {
     case 5: return sweep_fn_inst<2, 1>(s);
     case 8: return sweep_fn_inst<4, 0>(s);
     case 9: return sweep_fn_inst<4, 1>(s);
+    case 10: return sweep_fn_inst<4, 2>(s);
     case 16: return sweep_fn_inst<8, 0>(s);
     default: return sweep_fn_inst<8, 1>(s);
   }
@@ -375,7 +377,9 @@ struct Layout {
 
 static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin) {
   int cfg = (int)opt_tile_cfg.load();
-  if (cfg < 0 || cfg >= kNumTileCfgs) cfg = kDefaultTileCfg;
+  const bool automatic = cfg < 0 || cfg >= kNumTileCfgs;
+  if (automatic) cfg = (kb == 4 && stage_bytes <= 4 && opt_wide_tiles.load() != 0) ? kWideTileCfg : kDefaultTileCfg;
+  if (cfg == kWideTileCfg && (kb != 4 || stage_bytes > 4)) cfg = kDefaultTileCfg;  // (only instantiated for that shape)
   // fall back to the smaller tile if the staging buffer would not fit
   if (sweep_smem_bytes(kTileCfgs[cfg], stage_bytes) > smem_optin) cfg = 1;
   return cfg;
@@ -1178,6 +1182,7 @@ static std::atomic<int64_t> *find_opt(const char *name) {
   if (!strcmp(name, "first_atomic")) return &opt_first_atomic;
   if (!strcmp(name, "tma_keys")) return &opt_tma_keys;
   if (!strcmp(name, "prefetch_cols")) return &opt_prefetch_cols;
+  if (!strcmp(name, "wide_tiles")) return &opt_wide_tiles;
   if (!strcmp(name, "max_chunk")) return &opt_max_chunk;
   if (!strcmp(name, "bytewise")) return &opt_bytewise;
   if (!strcmp(name, "allow_skip")) return &opt_allow_skip;

@@ -12,7 +12,10 @@ struct TileCfg { int threads, ipt, minb; };
 // tile geometries of the scatter kernel (option "tile_cfg"); minb = CTAs per SM the kernel is compiled for.
 // (512x16x1 was measured slower in round 1, 256x16x4 -- four CTAs per SM at 64 registers -- no faster in either
 //  round: 8.13 vs 8.18 ms per pass at 1e9 records; both are gone: profiles/README.md)
-constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}};
+constexpr TileCfg kTileCfgs[] = {{256, 16, 3}, {256, 8, 4}, {256, 32, 3}};
+// (index 2: 8192-key tiles for 4-byte keys whose every stream moves in chunks of at most 4 bytes -- the same 32 KB
+//  of staging as 4096 8-byte keys, half the per-tile work (look-back, scans, tickets) per key; kb = 4 only)
+constexpr int kWideTileCfg = 2;
 constexpr int kNumTileCfgs = sizeof(kTileCfgs) / sizeof(kTileCfgs[0]);
 constexpr int kDefaultTileCfg = 0;
 
