@@ -375,10 +375,11 @@ struct Layout {
   int64_t n_tiles;
 };
 
-static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin) {
+static int pick_tile_cfg(int kb, uint32_t stage_bytes, size_t smem_optin, int64_t n) {
   int cfg = (int)opt_tile_cfg.load();
   const bool automatic = cfg < 0 || cfg >= kNumTileCfgs;
-  if (automatic) cfg = (kb == 4 && stage_bytes <= 4 && opt_wide_tiles.load() != 0) ? kWideTileCfg : kDefaultTileCfg;
+  // (wide tiles only where there are plenty of them: 10^6 records are 123 wide tiles for 148 SMs -- 0.18 vs 0.13 ms)
+  if (automatic) cfg = (kb == 4 && stage_bytes <= 4 && n >= ((int64_t)1 << 24) && opt_wide_tiles.load() != 0) ? kWideTileCfg : kDefaultTileCfg;
   if (cfg == kWideTileCfg && (kb != 4 || stage_bytes > 4)) cfg = kDefaultTileCfg;  // (only instantiated for that shape)
   // fall back to the smaller tile if the staging buffer would not fit
   if (sweep_smem_bytes(kTileCfgs[cfg], stage_bytes) > smem_optin) cfg = 1;
@@ -477,7 +478,7 @@ static int sort_device(int key_type, bool ascending, int64_t n, const std::vecto
     return fail(B200SORT_EINVAL, "record array is not aligned to its key type");
   if (((uintptr_t)streams[0].ptr % kb) != 0) return fail(B200SORT_EINVAL, "key array is not aligned to its key type");
 
-  const int cfg = pick_tile_cfg(kb, stage_bytes, di.smem_optin);
+  const int cfg = pick_tile_cfg(kb, stage_bytes, di.smem_optin, n);
   const TileCfg tc = kTileCfgs[cfg];
   const int tile = tc.threads * tc.ipt;
   const size_t smem = sweep_smem_bytes(tc, stage_bytes);

@@ -914,7 +914,7 @@ static int mgpu_sort(b200sort_comm *c, int key_type, const std::vector<StreamDes
     ss.streams[s].buf[0] = (unsigned char *)streams[s].ptr;
     stage_bytes = std::max(stage_bytes, ck);
   }
-  const int cfg = pick_tile_cfg(kb, stage_bytes, di.smem_optin);
+  const int cfg = pick_tile_cfg(kb, stage_bytes, di.smem_optin, num_local);
   const TileCfg tc = kTileCfgs[cfg];
   const int tile = tc.threads * tc.ipt;
   const int64_t n_ws = std::max<int64_t>(capacity, 1);

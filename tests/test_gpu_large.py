@@ -43,6 +43,20 @@ def test_c2_shape_default_options_2p25(golden_dir):
     assert bool((torch.sort(p).values == torch.arange(n, device="cuda")).all().item())  # ... and is a permutation
 
 
+def test_u32_u32_default_options_2p25_wide_tiles():
+    """config 1's shape (uint32 key + uint32 payload) at 2^25: the automatically chosen 8192-key tiles, plan read-back,
+    unstable first pass"""
+    n = N25
+    rng = np.random.default_rng(11)
+    keys = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    k, p = dev(keys), dev(np.arange(n, dtype=np.uint32))
+    S.sort(n, k, p, up=True)
+    torch.cuda.synchronize()
+    hk, hp = k.cpu().numpy(), p.cpu().numpy()
+    assert hk.tobytes() == np.sort(keys).tobytes()
+    assert keys[hp].tobytes() == hk.tobytes() and np.array_equal(np.sort(hp), np.arange(n, dtype=np.uint32))
+
+
 def test_c3_shape_default_options_2p25():
     """f32 key + (i32, f64, u16) payload streams, descending, with the SURVEY 8d edge set (configs[2] shape)"""
     n = N25

@@ -234,6 +234,26 @@ def test_tile_geometries_agree():
         S.set_option("tile_cfg", -1)
 
 
+def test_wide_tiles_for_4_byte_keys():
+    """8192-key tiles (tile geometry 2): chosen automatically for 4-byte keys with <= 4-byte chunks from 2^24 records
+    (test_gpu_large covers that size), forced here at sizes with full, partial and single tiles"""
+    try:
+        S.set_option("tile_cfg", 2)
+        for n in (5, 8191, 8193, 300_000, (1 << 22) + 4099):
+            for dt, up in ((np.uint32, True), (np.float32, False), (np.int32, False)):
+                keys = O.make_keys("Uniform" if n % 2 else "Gaussian", dt, n, seed=n % 97)
+                a, b = np.arange(n, dtype=np.uint32), (np.arange(n) % 251).astype(np.uint8)
+                for big in (24, 0):
+                    S.set_option("host_plan_min_log2", big)
+                    k, (pa, pb) = gpu_sort_soa(keys, [a, b], up)
+                    assert k.tobytes() == O.total_order_sorted_keys(keys, up).tobytes(), (n, dt, up, big)
+                    assert keys[pa].tobytes() == k.tobytes() and np.array_equal(np.sort(pa), a), (n, dt, up, big)
+                    assert np.array_equal(pb, (pa % 251).astype(np.uint8)), (n, dt, up, big)
+    finally:
+        S.set_option("tile_cfg", -1)
+        S.set_option("host_plan_min_log2", 24)
+
+
 @pytest.mark.parametrize("first_atomic", [0, 1])
 def test_unstable_first_pass_ranking(first_atomic):
     """large-sort flow: the first executed pass may rank with one shared-memory atomic per key (unstable);
