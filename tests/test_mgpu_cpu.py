@@ -240,3 +240,106 @@ def test_gloo_world2_refined_splitters_and_tie_split(tmp_path):
         outs.append(out)
     for rank, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"MGPU_SKEW_OK {rank}" in out, out[-3000:]
+
+
+# ------------------------------------------------------------------------------------------------
+# single-process unit tests of the same host logic: other world sizes (not a power of two), 1-/2-/4-byte keys
+# ------------------------------------------------------------------------------------------------
+def _split_and_count(keys_per_rank, world, n_blocks=64):
+    """runs b200sort_mgpu_refine_splitters + b200sort_mgpu_tie_thresholds over in-memory 'ranks' and returns the
+    number of records every destination gets (destination = upper bound over the (key, block) pairs)"""
+    import ctypes
+    import numpy as np
+    import simd_radix_sort_b200 as S
+    from simd_radix_sort_b200 import _api
+    L = S.lib()
+    kb = keys_per_rank[0].dtype.itemsize
+    total = sum(len(k) for k in keys_per_rank)
+    okeys = [k.astype(np.uint64) for k in keys_per_rank]      # (unsigned keys: their own ordered form)
+    keep = []
+
+    def hist_cb(ctx, n_ranges, lo, shift, nb, out):
+        h = np.zeros((n_ranges, 65536), np.uint64)
+        for j in range(n_ranges):
+            for u in okeys:
+                sel = u >= np.uint64(lo[j])
+                b = (u[sel] - np.uint64(lo[j])) >> np.uint64(shift[j])
+                b = b[b < np.uint64(nb[j])].astype(np.int64)
+                h[j] += np.bincount(b, minlength=65536).astype(np.uint64)
+        keep.append(h)
+        ctypes.memmove(out, h.ctypes.data, n_ranges * 65536 * 8)
+        return 0
+
+    ns = world - 1
+    keys_out, tie_out = np.zeros(max(ns, 1), np.uint64), np.zeros(max(ns, 1), np.uint32)
+    rc = L.b200sort_mgpu_refine_splitters(world, kb, total, _api.HIST_FN(hist_cb), None,
+                                          keys_out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                          tie_out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    assert rc == 0, L.b200sort_last_error()
+    keys_out, tie_out = keys_out[:ns], tie_out[:ns]
+    assert np.all(keys_out[1:] >= keys_out[:-1])
+    n_max = max(len(k) for k in keys_per_rank)
+    blk_shift = max(int(np.ceil(np.log2(max(n_max / n_blocks, 1)))), 0)
+    blk = np.zeros((world, max(ns, 1)), np.uint32)
+    for tv in np.unique(keys_out[tie_out != 0]):
+        less_total = int(sum(np.sum(u < tv) for u in okeys))
+        eq = np.zeros((world, n_blocks), np.uint32)
+        for s, u in enumerate(okeys):
+            pos = np.nonzero(u == tv)[0] >> blk_shift
+            eq[s] = np.bincount(pos, minlength=n_blocks)[:n_blocks]
+        which = np.nonzero((keys_out == tv) & (tie_out != 0))[0]
+        targets = np.array([(total * (int(r) + 1)) // world for r in which], np.uint64)
+        for rank in range(world):
+            out = np.zeros(len(which), np.uint32)
+            assert L.b200sort_mgpu_tie_thresholds(world, rank, n_blocks, less_total, eq.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                  len(which), targets.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) == 0
+            blk[rank, which] = out
+    sizes = np.zeros(world, np.int64)
+    lo_hi = []
+    for rank, u in enumerate(okeys):
+        b = (np.arange(len(u)) >> blk_shift).astype(np.uint32)
+        dest = np.zeros(len(u), np.int64)
+        for r in range(ns):
+            dest += ((u > keys_out[r]) | ((u == keys_out[r]) & (b >= blk[rank, r]))).astype(np.int64)
+        sizes += np.bincount(dest, minlength=world)
+        lo_hi.append((u, dest))
+    # destinations are monotonic in the key
+    mins = np.full(world, np.iinfo(np.uint64).max, np.uint64)
+    maxs = np.zeros(world, np.uint64)
+    for u, dest in lo_hi:
+        for d in range(world):
+            sel = dest == d
+            if sel.any():
+                mins[d] = min(mins[d], u[sel].min())
+                maxs[d] = max(maxs[d], u[sel].max())
+    last = None
+    for d in range(world):
+        if sizes[d]:
+            if last is not None:
+                assert maxs[last] <= mins[d]
+            last = d
+    return sizes, total
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+@pytest.mark.parametrize("case", ["zero_u8", "two_values_u16", "uniform_u32", "heavy_30pct_u64", "geometric_u16", "distinct_close_u64"])
+def test_refined_splitters_balance_any_world(world, case):
+    import numpy as np
+    n = 30_000
+    rngs = [np.random.default_rng(100 * world + r) for r in range(world)]
+    if case == "zero_u8":
+        ranks = [np.zeros(n + 17 * r, np.uint8) for r in range(world)]
+    elif case == "two_values_u16":
+        ranks = [np.where(g.random(n) < 0.3, 7, 40000).astype(np.uint16) for g in rngs]
+    elif case == "uniform_u32":
+        ranks = [g.integers(0, 2**32, size=n, dtype=np.uint32) for g in rngs]
+    elif case == "heavy_30pct_u64":
+        ranks = [np.where(g.random(n) < 0.3, np.uint64(1) << np.uint64(63), g.integers(0, 2**64, size=n, dtype=np.uint64)) for g in rngs]
+    elif case == "geometric_u16":
+        ranks = [np.minimum(g.geometric(0.05, size=n), 65535).astype(np.uint16) for g in rngs]
+    else:  # distinct keys that differ only in their lowest bits: refinement must go all the way down, no ties
+        ranks = [(np.uint64(0xABCD) << np.uint64(48)) + g.permutation(n).astype(np.uint64) + np.uint64(r * n) for r, g in enumerate(rngs)]
+    sizes, total = _split_and_count(ranks, world)
+    assert sizes.sum() == total
+    assert sizes.max() <= 1.125 * total / world + 1, (case, world, sizes.tolist())
