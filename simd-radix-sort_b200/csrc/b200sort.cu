@@ -444,11 +444,11 @@ struct DevSortOpts {
 };
 constexpr int64_t CMP_NONE_MIN_THRESH = 8;  // below it nearly every sort would need the finish anyway: full sort
 
-// one event per device for the plan read-back of large sorts (an event belongs to the device it was created on)
+// one event per (host thread, device) for the plan read-back of large sorts: an event belongs to the device it was
+// created on, and two host threads sorting on one device (with their own workspaces) must not share one
 static cudaEvent_t plan_event_of(int dev) {
-  static std::map<int, cudaEvent_t> g_plan_events;
-  std::lock_guard<std::mutex> lk(g_mu);
-  cudaEvent_t &e = g_plan_events[dev];
+  static thread_local std::map<int, cudaEvent_t> t_plan_events;
+  cudaEvent_t &e = t_plan_events[dev];
   if (e == nullptr && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) e = nullptr;
   return e;
 }
